@@ -1,0 +1,188 @@
+/*
+ * b2s.h - C ABI of libb2s.so, the B200-native (sm_100a) sparse-voxel backend.
+ *
+ * This is the drop-in boundary for the hot path of PJLab-ADG/OpenPCSeg: it
+ * replaces the pybind11 module `torchsparse.backend` of the torchsparse 1.4.0
+ * bundled in the reference (`package/torchsparse.zip`, written TS/ below =
+ * `torchsparse/torchsparse/` inside the zip; the 20 bound functions are listed
+ * at TS/backend/pybind_cuda.cpp:18-39) plus RPVNet's `range_utils` ops
+ * (pcseg/model/segmentor/fusion/rpvnet/range_lib/range_utils/src/
+ * rangelib_bindings_gpu.cpp:7-12).
+ *
+ * Conventions
+ *  - plain pointers + sizes, no torch / ATen types.  Every pointer is a DEVICE
+ *    pointer unless the parameter name ends in `_host`.
+ *  - every entry point is stream-ordered on `stream` (a cudaStream_t), never
+ *    synchronises the device, never allocates: outputs and workspaces are
+ *    provided by the caller; `*_bytes` functions size the workspaces.
+ *  - return value: 0 = B2S_OK, otherwise a b2s_status; b2s_last_error() gives
+ *    a thread-local message.  Nothing throws.
+ *  - row-major everywhere.  Coordinates are int32 [N,4] = (x, y, z, batch)
+ *    exactly like the reference (TS/tensor.py:10-24).
+ *  - `dtype` selects the feature element type: B2S_F32 or B2S_F16.
+ */
+#ifndef B2S_H_
+#define B2S_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* b2s_stream_t; /* cudaStream_t */
+
+enum b2s_status {
+  B2S_OK = 0,
+  B2S_ERR_INVALID = 1,     /* bad argument (shape, null pointer, unsupported dtype) */
+  B2S_ERR_WORKSPACE = 2,   /* workspace too small */
+  B2S_ERR_CUDA = 3,        /* CUDA runtime error at launch */
+  B2S_ERR_UNSUPPORTED = 4  /* shape not supported by this kernel family */
+};
+enum b2s_dtype { B2S_F32 = 0, B2S_F16 = 1 };
+
+const char* b2s_last_error(void);
+int b2s_version(void);
+
+/* ---------------------------------------------------------------- hashing ---
+ * replaces hash_cuda / kernel_hash_cuda (TS/backend/hash/hash_cuda.cu:67-84).
+ * out[i]       = fold60(fnv1a_words(x, y, z, b))
+ * out[k*n + i] = same for (x+off[k][0], y+off[k][1], z+off[k][2], b)          */
+int b2s_hash(const int32_t* coords, int64_t n, int64_t* out, b2s_stream_t stream);
+int b2s_kernel_hash(const int32_t* coords, int64_t n, const int32_t* offsets, int32_t k,
+                    int64_t* out, b2s_stream_t stream);
+
+/* ------------------------------------------------------------- hash table ---
+ * replaces hash_query_cuda (TS/backend/others/query_cuda.cu:9-56 and the cuckoo
+ * table in TS/backend/hashmap/hashmap_cuda.cu).  Open addressing, 64-bit keys,
+ * value = row index of the key in `references`; duplicate keys resolve to the
+ * smallest row index (the CPU reference's first-insert-wins,
+ * TS/backend/others/query_cpu.cpp:22-26).  The key -1 is reserved (sphash values are < 2^60).
+ * out[i] = index or -1 (the value sphashquery returns, TS/nn/functional/query.py:32). */
+int64_t b2s_table_slots(int64_t n_references);
+size_t b2s_table_bytes(int64_t n_references);
+int b2s_table_build(const int64_t* references, int64_t n, void* table, size_t table_bytes,
+                    b2s_stream_t stream);
+int b2s_table_build_coords(const int32_t* coords, int64_t n, void* table, size_t table_bytes,
+                           b2s_stream_t stream); /* keys = b2s_hash(coords), fused */
+int b2s_table_query(const void* table, int64_t n_references, const int64_t* queries, int64_t nq,
+                    int64_t* out, b2s_stream_t stream);
+
+/* replaces count_cuda (TS/backend/others/count_cuda.cu:25-31); zero-fills out first. */
+int b2s_count(const int32_t* idx, int64_t n, int32_t* out, int64_t num, b2s_stream_t stream);
+
+/* -------------------------------------------------- sorted unique / coords ---
+ * b2s_unique_i64: ascending unique of int64 keys (what torch.unique(pc_hash)
+ * does in pcseg/model/segmentor/voxel/minkunet/utils.py:17).  d_count[0]
+ * receives the number of unique keys.
+ * b2s_downsample_coords: output coordinates of a strided conv, sorted by
+ * (batch, x, y, z) and unique - replaces spdownsample
+ * (TS/nn/functional/downsample.py:11-52), both the snap-to-grid fast path and
+ * the kernel-expansion slow path.  `out_coords` must hold n rows (fast path) or
+ * n*kernel_volume rows (slow path); d_count[0] = rows written, d_count[1] = 0 or
+ * 1 if a coordinate fell outside the packable range (|xyz| < 2^17, 0 <= b < 1024). */
+size_t b2s_unique_workspace_bytes(int64_t n);
+int b2s_unique_i64(const int64_t* keys, int64_t n, int64_t* out, int64_t* d_count, void* ws,
+                   size_t ws_bytes, b2s_stream_t stream);
+int64_t b2s_downsample_capacity(int64_t n, const int32_t* stride_host,
+                                const int32_t* kernel_host);
+size_t b2s_downsample_workspace_bytes(int64_t n, const int32_t* stride_host,
+                                      const int32_t* kernel_host);
+int b2s_downsample_coords(const int32_t* coords, int64_t n, const int32_t* stride_host,
+                          const int32_t* kernel_host, const int32_t* tensor_stride_host,
+                          int32_t* out_coords, int64_t* d_count, void* ws, size_t ws_bytes,
+                          b2s_stream_t stream);
+
+/* ------------------------------------------------------------- kernel map ---
+ * Fused replacement of sphash + kernel-hash + sphashquery + nonzero
+ * (TS/nn/functional/conv.py:156-176).  Pair convention of the reference:
+ * in_coord = out_coord + offset[k].
+ *   nbr_out [K, n_out] int32 : input row feeding output row o through W[k], or -1
+ *   nbr_in  [K, n_in ] int32 : output row fed by input row i through W[k], or -1
+ *                              (may be NULL)
+ *   nbsizes [K] int32        : pairs per offset
+ * b2s_kmap_pairs then emits the reference-format pair list: nbmaps int32 [M,2] =
+ * (in, out), grouped by k ascending, out ascending inside a group; d_total[0]=M.
+ * `nbmaps` must hold K*n_out rows.                                            */
+size_t b2s_kmap_workspace_bytes(int64_t n_in, int64_t n_out, int32_t k);
+int b2s_kmap_build(const int32_t* in_coords, int64_t n_in, const int32_t* out_coords,
+                   int64_t n_out, const int32_t* offsets, int32_t k, int32_t* nbr_out,
+                   int32_t* nbr_in, int32_t* nbsizes, void* ws, size_t ws_bytes,
+                   b2s_stream_t stream);
+int b2s_kmap_pairs(const int32_t* nbr_out, int32_t k, int64_t n_out, int32_t* nbmaps,
+                   int64_t* d_total, void* ws, size_t ws_bytes, b2s_stream_t stream);
+
+/* ------------------------------------------------------------ convolution ---
+ * replaces convolution_forward_cuda / convolution_backward_cuda
+ * (TS/backend/convolution/convolution_cuda.cu:53-165, :167-278).
+ *
+ * b2s_conv_gather_gemm: out[r, :] = sum_k in[nbr[kk(k)][r], :] * B_k   for r < n_rows
+ *   where nbr is [K, n_rows] (rows with -1 contribute nothing), kk(k) = flip_k ?
+ *   K-1-k : k, and B_k = weight[k] ([c_in, c_out]) when transpose_w == 0
+ *   (forward: c_red = c_in, c_res = c_out) or weight[k]^T when transpose_w == 1
+ *   (input gradient: c_red = c_out, c_res = c_in).  fp32 accumulation over all
+ *   offsets, one write per output row, no atomics, deterministic.
+ *   `in` has n_src rows of c_red channels; `out` n_rows x c_res; optional bias[c_res].
+ * b2s_conv_wgrad: grad_w[k] = sum over pairs of offset k of in[i]^T * grad_out[o],
+ *   pairs from b2s_kmap_pairs (device-resident sizes, no host sync).  grad_w is
+ *   fp32 [K, c_in, c_out] and is zero-filled by the call.
+ * `weight` has the feature dtype; k = 1 expresses the 1x1 / dense case with
+ * nbr == NULL (identity map).                                                  */
+size_t b2s_conv_workspace_bytes(int32_t dtype, int64_t n_rows, int32_t c_in, int32_t c_out,
+                                int32_t k);
+int b2s_conv_gather_gemm(int32_t dtype, const void* in, int64_t n_src, const void* weight,
+                         int32_t k, int32_t c_in, int32_t c_out, int32_t transpose_w,
+                         int32_t flip_k, const int32_t* nbr, int64_t n_rows, const void* bias,
+                         void* out, void* ws, size_t ws_bytes, b2s_stream_t stream);
+int b2s_conv_wgrad(int32_t dtype, const void* in, int64_t n_in, const void* grad_out,
+                   int64_t n_out, int32_t k, int32_t c_in, int32_t c_out, const int32_t* nbmaps,
+                   const int32_t* nbsizes, int32_t swap_pairs, float* grad_w, void* ws,
+                   size_t ws_bytes, b2s_stream_t stream);
+
+/* --------------------------------------------------------- point <-> voxel ---
+ * replaces voxelize_{forward,backward}_cuda (TS/backend/voxelize/voxelize_cuda.cu:44-80)
+ * and devoxelize_{forward,backward}_cuda (TS/backend/devoxelize/devoxelize_cuda.cu:61-98).
+ * `acc` is an fp32 scratch [n_vox, c] needed when dtype == B2S_F16 for the
+ * scatter-adds (NULL for B2S_F32: the output itself is the accumulator).       */
+int b2s_voxelize_fwd(int32_t dtype, const void* feats, const int32_t* idx, const int32_t* counts,
+                     int64_t n_pts, int64_t n_vox, int32_t c, void* out, float* acc,
+                     b2s_stream_t stream);
+int b2s_voxelize_bwd(int32_t dtype, const void* grad_vox, const int32_t* idx,
+                     const int32_t* counts, int64_t n_pts, int64_t n_vox, int32_t c,
+                     void* grad_pts, b2s_stream_t stream);
+int b2s_devoxelize_fwd(int32_t dtype, const void* feats, const int32_t* idx /*[n_pts,8]*/,
+                       const void* weights /*[n_pts,8], feature dtype*/, int64_t n_pts,
+                       int64_t n_vox, int32_t c, void* out, b2s_stream_t stream);
+int b2s_devoxelize_bwd(int32_t dtype, const void* grad_pts, const int32_t* idx,
+                       const void* weights, int64_t n_pts, int64_t n_vox, int32_t c,
+                       void* grad_vox, float* acc, b2s_stream_t stream);
+
+/* Fused voxel_to_point map (pcseg/model/segmentor/voxel/minkunet/utils.py:73-81 +
+ * calc_ti_weights, TS/nn/functional/devoxelize.py:10-48): for every point, the 8
+ * corner voxel rows (or -1) at `stride` and the fp32 trilinear weights.
+ * pts: fp32 [n_pts,4] = (x, y, z, batch) in voxel units; table built over the
+ * voxel coords with b2s_table_build_coords.  idx int32 [n_pts,8], w fp32 [n_pts,8]. */
+int b2s_trilinear_map(const float* pts, int64_t n_pts, int32_t stride, const void* table,
+                      int64_t n_vox, int32_t* idx, float* w, b2s_stream_t stream);
+/* calc_ti_weights alone: idx is the reference-layout int64 [8, n_pts]; w fp32 [8, n_pts]. */
+int b2s_ti_weights(const float* pts, int64_t n_pts, const int64_t* idx, float scale, float* w,
+                   b2s_stream_t stream);
+
+/* --------------------------------------------------------- range-image ops ---
+ * RPVNet: replaces map_count_forward / denselize_forward / denselize_backward
+ * (range_lib/range_utils/src/map_count_gpu.cu:5-14, denselize_gpu.cu:5-34).
+ * pxpy int32 [n,3] = (batch, px, py); count_map int32 [B,1,H,W]; dense fp32 [B,C,H,W]. */
+int b2s_map_count(const int32_t* pxpy, int64_t n, int32_t b, int32_t h, int32_t w,
+                  int32_t* count_map, b2s_stream_t stream);
+int b2s_denselize_fwd(const float* feats, const int32_t* pxpy, const int32_t* count_map,
+                      int64_t n, int32_t c, int32_t b, int32_t h, int32_t w, float* dense,
+                      b2s_stream_t stream);
+int b2s_denselize_bwd(const float* grad_dense, const int32_t* pxpy, const int32_t* count_map,
+                      int64_t n, int32_t c, int32_t b, int32_t h, int32_t w, float* grad_feats,
+                      b2s_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2S_H_ */
