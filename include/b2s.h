@@ -152,10 +152,10 @@ int b2s_voxelize_bwd(int32_t dtype, const void* grad_vox, const int32_t* idx,
                      const int32_t* counts, int64_t n_pts, int64_t n_vox, int32_t c,
                      void* grad_pts, b2s_stream_t stream);
 int b2s_devoxelize_fwd(int32_t dtype, const void* feats, const int32_t* idx /*[n_pts,8]*/,
-                       const void* weights /*[n_pts,8], feature dtype*/, int64_t n_pts,
+                       const float* weights /*[n_pts,8] fp32*/, int64_t n_pts,
                        int64_t n_vox, int32_t c, void* out, b2s_stream_t stream);
 int b2s_devoxelize_bwd(int32_t dtype, const void* grad_pts, const int32_t* idx,
-                       const void* weights, int64_t n_pts, int64_t n_vox, int32_t c,
+                       const float* weights, int64_t n_pts, int64_t n_vox, int32_t c,
                        void* grad_vox, float* acc, b2s_stream_t stream);
 
 /* Fused voxel_to_point map (pcseg/model/segmentor/voxel/minkunet/utils.py:73-81 +

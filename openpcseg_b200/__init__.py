@@ -1,0 +1,24 @@
+"""openpcseg_b200: B200-native (sm_100a) sparse-voxel convolution backend that drops in
+under OpenPCSeg's voxel / fusion segmentors behind the torchsparse operator surface.
+
+    import openpcseg_b200
+    openpcseg_b200.install_as_torchsparse()   # `import torchsparse` now resolves here
+"""
+import sys
+
+__all__ = ["install_as_torchsparse"]
+
+
+def install_as_torchsparse() -> None:
+    """Alias ``openpcseg_b200.torchsparse`` (and submodules) as ``torchsparse`` so that
+    reference model code (`import torchsparse.nn as spnn`, ...) runs unmodified."""
+    import importlib
+
+    pkg = importlib.import_module("openpcseg_b200.torchsparse")
+    prefix = "openpcseg_b200.torchsparse"
+    for name in ["", ".nn", ".nn.functional", ".nn.utils", ".nn.modules", ".utils", ".utils.collate",
+                 ".utils.quantize", ".tensor", ".operators"]:
+        sys.modules["torchsparse" + name] = importlib.import_module(prefix + name)
+    from . import backend
+    sys.modules["torchsparse.backend"] = backend
+    pkg.backend = backend

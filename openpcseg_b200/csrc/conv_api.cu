@@ -1,0 +1,115 @@
+// C-ABI entry points of the sparse convolution; dispatches between the tensor-core
+// (conv_tc.cu, fp16, tcgen05) and the CUDA-core (conv_simt.cu, exact fp32) kernel families.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace b2s {
+template <typename T>
+int launch_gather_gemm_simt(const void* in, const void* weight, int k, int c_in, int c_out,
+                            int transpose_w, int flip_k, const int32_t* nbr, int64_t n_rows,
+                            const void* bias, void* out, cudaStream_t st);
+template <typename T>
+int launch_wgrad_simt(const void* in, const void* gout, const int32_t* nbmaps,
+                      const int32_t* nbsizes, int64_t n_identity, int64_t n_pairs_bound, int k,
+                      int c_in, int c_out, int swap_pairs, float* gw, cudaStream_t st);
+
+// conv_tc.cu
+bool tc_gather_gemm_supported(int c_red, int c_res);
+int launch_gather_gemm_tc(const void* in, const void* weight, int k, int c_in, int c_out,
+                          int transpose_w, int flip_k, const int32_t* nbr, int64_t n_rows,
+                          const void* bias, void* out, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t tc_gather_gemm_workspace(int k, int c_in, int c_out);
+bool tc_wgrad_supported(int c_in, int c_out);
+int launch_wgrad_tc(const void* in, const void* gout, const int32_t* nbmaps,
+                    const int32_t* nbsizes, int64_t n_identity, int64_t n_pairs_bound, int k,
+                    int c_in, int c_out, int swap_pairs, float* gw, cudaStream_t st);
+
+static bool force_simt() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2S_FORCE_SIMT");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+}  // namespace b2s
+
+using namespace b2s;
+
+extern "C" {
+
+size_t b2s_conv_workspace_bytes(int32_t dtype, int64_t n_rows, int32_t c_in, int32_t c_out,
+                                int32_t k) {
+  (void)n_rows;
+  if (dtype != B2S_F16) return 0;
+  return tc_gather_gemm_workspace(k, c_in, c_out);
+}
+
+int b2s_conv_gather_gemm(int32_t dtype, const void* in, int64_t n_src, const void* weight,
+                         int32_t k, int32_t c_in, int32_t c_out, int32_t transpose_w,
+                         int32_t flip_k, const int32_t* nbr, int64_t n_rows, const void* bias,
+                         void* out, void* ws, size_t ws_bytes, b2s_stream_t stream) {
+  B2S_REQUIRE(dtype == B2S_F32 || dtype == B2S_F16, B2S_ERR_INVALID, "b2s_conv_gather_gemm: dtype");
+  B2S_REQUIRE(k >= 1 && c_in >= 1 && c_out >= 1 && n_rows >= 0 && n_src >= 0, B2S_ERR_INVALID,
+              "b2s_conv_gather_gemm: bad sizes");
+  B2S_REQUIRE(nbr || k == 1, B2S_ERR_INVALID,
+              "b2s_conv_gather_gemm: nbr == NULL (identity map) needs k == 1");
+  B2S_REQUIRE(nbr || n_rows <= n_src, B2S_ERR_INVALID,
+              "b2s_conv_gather_gemm: identity map with n_rows > n_src");
+  if (n_rows == 0) return B2S_OK;
+  B2S_REQUIRE(in && weight && out, B2S_ERR_INVALID, "b2s_conv_gather_gemm: null pointer");
+  B2S_REQUIRE(n_rows < (1LL << 31) && n_src < (1LL << 31), B2S_ERR_UNSUPPORTED,
+              "b2s_conv_gather_gemm: more than 2^31 rows");
+  cudaStream_t st = as_stream(stream);
+  const int c_red = transpose_w ? c_out : c_in, c_res = transpose_w ? c_in : c_out;
+  if (dtype == B2S_F16 && !force_simt() && tc_gather_gemm_supported(c_red, c_res)) {
+    int rc = launch_gather_gemm_tc(in, weight, k, c_in, c_out, transpose_w, flip_k, nbr, n_rows,
+                                   bias, out, ws, ws_bytes, st);
+    if (rc != B2S_OK) return rc;
+  } else if (dtype == B2S_F16) {
+    launch_gather_gemm_simt<__half>(in, weight, k, c_in, c_out, transpose_w, flip_k, nbr, n_rows,
+                                    bias, out, st);
+  } else {
+    launch_gather_gemm_simt<float>(in, weight, k, c_in, c_out, transpose_w, flip_k, nbr, n_rows,
+                                   bias, out, st);
+  }
+  B2S_CHECK_LAUNCH("b2s_conv_gather_gemm");
+  return B2S_OK;
+}
+
+int b2s_conv_wgrad(int32_t dtype, const void* in, int64_t n_in, const void* grad_out,
+                   int64_t n_out, int32_t k, int32_t c_in, int32_t c_out, const int32_t* nbmaps,
+                   const int32_t* nbsizes, int32_t swap_pairs, float* grad_w, void* ws,
+                   size_t ws_bytes, b2s_stream_t stream) {
+  (void)ws;
+  (void)ws_bytes;
+  B2S_REQUIRE(dtype == B2S_F32 || dtype == B2S_F16, B2S_ERR_INVALID, "b2s_conv_wgrad: dtype");
+  B2S_REQUIRE(k >= 1 && c_in >= 1 && c_out >= 1 && n_in >= 0 && n_out >= 0 && grad_w,
+              B2S_ERR_INVALID, "b2s_conv_wgrad: bad argument");
+  B2S_REQUIRE((nbmaps && nbsizes) || k == 1, B2S_ERR_INVALID,
+              "b2s_conv_wgrad: pair list required unless k == 1 (identity)");
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(grad_w, 0, (size_t)k * c_in * c_out * sizeof(float), st);
+  if (n_in == 0 || n_out == 0) return B2S_OK;
+  B2S_REQUIRE(in && grad_out, B2S_ERR_INVALID, "b2s_conv_wgrad: null pointer");
+  // upper bound of the number of pairs (only used to size the grid)
+  const int64_t rows = swap_pairs ? n_in : n_out;
+  const int64_t bound = nbmaps ? rows * k : (n_in < n_out ? n_in : n_out);
+  const int64_t n_identity = n_in < n_out ? n_in : n_out;
+  if (dtype == B2S_F16 && !force_simt() && tc_wgrad_supported(c_in, c_out)) {
+    int rc = launch_wgrad_tc(in, grad_out, nbmaps, nbsizes, n_identity, bound, k, c_in, c_out,
+                             swap_pairs, grad_w, st);
+    if (rc != B2S_OK) return rc;
+  } else if (dtype == B2S_F16) {
+    launch_wgrad_simt<__half>(in, grad_out, nbmaps, nbsizes, n_identity, bound, k, c_in, c_out,
+                              swap_pairs, grad_w, st);
+  } else {
+    launch_wgrad_simt<float>(in, grad_out, nbmaps, nbsizes, n_identity, bound, k, c_in, c_out,
+                             swap_pairs, grad_w, st);
+  }
+  B2S_CHECK_LAUNCH("b2s_conv_wgrad");
+  return B2S_OK;
+}
+
+}  // extern "C"

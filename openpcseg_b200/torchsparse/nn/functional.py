@@ -1,0 +1,286 @@
+"""torchsparse.nn.functional surface over libb2s (reference: TS/nn/functional/*.py).
+
+Differences from the reference that are deliberate and invisible in results:
+  * a kernel map is ONE fused device pass (table build + K probes per output row) that
+    yields gather maps ``nbr_out`` / ``nbr_in``; the reference's ``[M, 2]`` pair list is
+    derived from it in the same order and is only materialised for wgrad / inspection;
+  * the convolution accumulates all kernel offsets in fp32 and writes each output row
+    once (the reference accumulates across offsets in the storage dtype);
+  * no host synchronisation inside conv forward/backward (the reference copies
+    ``nbsizes`` to the host for every call, TS/nn/functional/conv.py:56,103).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple, Union
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from ... import backend as B
+from ..tensor import SparseTensor
+from ..utils import make_ntuple
+from .utils import fapply, get_kernel_offsets
+
+__all__ = ["sphash", "sphashquery", "spcount", "spdownsample", "spvoxelize", "spdevoxelize",
+           "calc_ti_weights", "conv3d", "relu", "leaky_relu", "KernelMap", "build_kernel_map"]
+
+
+# ------------------------------------------------------------------ hash / query / count
+def sphash(coords: torch.Tensor, offsets: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """TS/nn/functional/hash.py:10-37."""
+    assert coords.dtype == torch.int, coords.dtype
+    assert coords.ndim == 2 and coords.shape[1] == 4, coords.shape
+    if offsets is None:
+        return B.hash_coords(coords)
+    assert offsets.dtype == torch.int, offsets.dtype
+    assert offsets.ndim == 2 and offsets.shape[1] == 3, offsets.shape
+    return B.kernel_hash(coords, offsets)
+
+
+def sphashquery(queries: torch.Tensor, references: torch.Tensor) -> torch.Tensor:
+    """Index of each query hash in ``references`` or -1 (TS/nn/functional/query.py:8-33)."""
+    shape = queries.size()
+    return B.hash_query(queries.contiguous().view(-1), references.contiguous()).view(*shape)
+
+
+def spcount(coords: torch.Tensor, num) -> torch.Tensor:
+    """TS/nn/functional/count.py:8-16."""
+    return B.count(coords.contiguous(), int(num))
+
+
+def spdownsample(coords: torch.Tensor, stride=2, kernel_size=2, tensor_stride=1) -> torch.Tensor:
+    """TS/nn/functional/downsample.py:11-52 (one device pass + one host sync for the count)."""
+    return B.downsample_coords(coords, make_ntuple(stride, 3), make_ntuple(kernel_size, 3),
+                               make_ntuple(tensor_stride, 3))
+
+
+# ------------------------------------------------------------------- point <-> voxel
+def _amp_half(t: torch.Tensor) -> torch.Tensor:
+    """custom_fwd(cast_inputs=torch.half) of the reference: under CUDA autocast the feature
+    operand runs in fp16 (TS/nn/functional/voxelize.py:13, devoxelize.py:54, conv.py:19)."""
+    if torch.is_autocast_enabled() and t.is_floating_point() and t.dtype != torch.float16:
+        return t.half()
+    return t
+
+
+class _Voxelize(Function):
+    @staticmethod
+    def forward(ctx, feats, idx, counts):
+        ctx.aux = (idx, counts, feats.shape[0])
+        return B.voxelize_forward(feats, idx, counts)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad):
+        idx, counts, n = ctx.aux
+        return B.voxelize_backward(grad.contiguous(), idx, counts, n), None, None
+
+
+def spvoxelize(feats: torch.Tensor, coords: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+    """Scatter-mean of point rows into voxel rows (TS/nn/functional/voxelize.py:10-56)."""
+    return _Voxelize.apply(_amp_half(feats), coords.contiguous().int(), counts.contiguous())
+
+
+class _Devoxelize(Function):
+    @staticmethod
+    def forward(ctx, feats, idx, weights):
+        ctx.aux = (idx, weights, feats.shape[0])
+        return B.devoxelize_forward(feats, idx, weights)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad):
+        idx, weights, n_vox = ctx.aux
+        return B.devoxelize_backward(grad.contiguous(), idx, weights, n_vox), None, None
+
+
+def spdevoxelize(feats: torch.Tensor, coords: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+    """Trilinear gather voxels -> points (TS/nn/functional/devoxelize.py:51-98); weights stay fp32."""
+    return _Devoxelize.apply(_amp_half(feats), coords.contiguous().int(),
+                             weights.detach().float().contiguous())
+
+
+def calc_ti_weights(coords: torch.Tensor, idx_query: torch.Tensor, scale: float = 1) -> torch.Tensor:
+    """fp32 [8, N] trilinear weights (TS/nn/functional/devoxelize.py:10-48), one kernel."""
+    with torch.no_grad():
+        return B.ti_weights(coords, idx_query, float(scale))
+
+
+# ----------------------------------------------------------------------- kernel map
+class KernelMap:
+    """Device-resident rule set of one (stride, kernel, conv-stride, dilation) key.
+
+    Behaves like the reference's ``[nbmaps, nbsizes, (N_in, N_out)]`` list
+    (TS/nn/functional/conv.py:174-176) when indexed or unpacked; the int64 ``nbmaps``
+    view is materialised lazily (one host sync) because the kernels here consume the
+    gather maps and the padded int32 pair buffer directly.
+    """
+
+    def __init__(self, nbr_out, nbr_in, nbsizes, sizes: Tuple[int, int], symmetric: bool):
+        self.nbr_out = nbr_out          # int32 [K, N_out]: input row per (offset, output row)
+        self.nbr_in = nbr_in            # int32 [K, N_in ]: output row per (offset, input row) | None
+        self.nbsizes32 = nbsizes        # int32 [K] on device
+        self.sizes = sizes
+        self.symmetric = symmetric      # nbr_in[k] == nbr_out[K-1-k] (submanifold, odd kernel)
+        self.kvol = nbr_out.shape[0]
+        self._pairs = None              # (int32 [K*N_out, 2] padded, int64 [1] total)
+        self._ref = None
+
+    def pairs(self):
+        if self._pairs is None:
+            self._pairs = B.kmap_pairs(self.nbr_out)
+        return self._pairs
+
+    def in_gather_map(self) -> Tuple[torch.Tensor, bool]:
+        """(map [K, N_in], flip_k) giving, per input row, the output row it feeds."""
+        if self.symmetric:
+            return self.nbr_out, True
+        return self.nbr_in, False
+
+    def reference_format(self):
+        if self._ref is None:
+            pairs, total = self.pairs()
+            m = int(total.item())
+            self._ref = [pairs[:m].long(), self.nbsizes32.long(), self.sizes]
+        return self._ref
+
+    def __getitem__(self, i):
+        return self.reference_format()[i]
+
+    def __iter__(self):
+        return iter(self.reference_format())
+
+    def __len__(self):
+        return 3
+
+
+def build_kernel_map(in_coords: torch.Tensor, out_coords: torch.Tensor, kernel_size, in_stride,
+                     dilation=1) -> KernelMap:
+    kernel_size = make_ntuple(kernel_size, 3)
+    offsets = get_kernel_offsets(kernel_size, stride=in_stride, dilation=dilation,
+                                 device=in_coords.device)
+    same = (in_coords is out_coords) or (in_coords.data_ptr() == out_coords.data_ptr()
+                                          and in_coords.shape == out_coords.shape)
+    symmetric = bool(same and all(k % 2 == 1 for k in kernel_size))
+    nbr_out, nbr_in, nbsizes = B.kmap_build(in_coords, out_coords, offsets, want_nbr_in=not symmetric)
+    return KernelMap(nbr_out, nbr_in, nbsizes, (in_coords.shape[0], out_coords.shape[0]), symmetric)
+
+
+# ---------------------------------------------------------------------- convolution
+class ConvolutionFunction(Function):
+    """out = sum_k gather(in, map_k) @ W[k]  (TS/nn/functional/conv.py:16-119).
+
+    ``weight`` keeps its parameter dtype (fp32 master); it is cast to the feature dtype
+    here and its gradient is returned in fp32 straight from the wgrad kernel.
+    """
+
+    @staticmethod
+    def forward(ctx, feats, weight, kmap: KernelMap, transposed: bool):
+        feats = feats.contiguous()
+        w = weight.to(feats.dtype)
+        if not transposed:
+            out = B.conv_gather_gemm(feats, w, kmap.nbr_out, kmap.sizes[1], False, False)
+        else:
+            gmap, flip = kmap.in_gather_map()
+            out = B.conv_gather_gemm(feats, w, gmap, kmap.sizes[0], False, flip)
+        ctx.save_for_backward(feats, weight)
+        ctx.kmap, ctx.transposed = kmap, transposed
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        feats, weight = ctx.saved_tensors
+        kmap, transposed = ctx.kmap, ctx.transposed
+        grad_out = grad_out.contiguous()
+        w = weight.to(feats.dtype)
+        grad_in = grad_w = None
+        if ctx.needs_input_grad[0]:
+            if not transposed:
+                gmap, flip = kmap.in_gather_map()
+                grad_in = B.conv_gather_gemm(grad_out, w, gmap, kmap.sizes[0], True, flip)
+            else:
+                grad_in = B.conv_gather_gemm(grad_out, w, kmap.nbr_out, kmap.sizes[1], True, False)
+        if ctx.needs_input_grad[1]:
+            pairs, _ = kmap.pairs()
+            grad_w = B.conv_wgrad(feats, grad_out, kmap.kvol, pairs, kmap.nbsizes32, transposed)
+            grad_w = grad_w.to(weight.dtype)
+        return grad_in, grad_w, None, None
+
+
+class _DenseConv(Function):
+    """1x1x1 conv = per-row GEMM through the same kernel family (identity map)."""
+
+    @staticmethod
+    def forward(ctx, feats, weight):
+        feats = feats.contiguous()
+        ctx.save_for_backward(feats, weight)
+        return B.conv_gather_gemm(feats, weight.to(feats.dtype), None, feats.shape[0], False, False)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        feats, weight = ctx.saved_tensors
+        grad_out = grad_out.contiguous()
+        grad_in = grad_w = None
+        if ctx.needs_input_grad[0]:
+            grad_in = B.conv_gather_gemm(grad_out, weight.to(feats.dtype), None, feats.shape[0], True,
+                                         False)
+        if ctx.needs_input_grad[1]:
+            grad_w = B.conv_wgrad(feats, grad_out, 1, None, None, False)[0].to(weight.dtype)
+        return grad_in, grad_w
+
+
+def conv3d(input: SparseTensor, weight: torch.Tensor,
+           kernel_size: Union[int, List[int], Tuple[int, ...]], bias: Optional[torch.Tensor] = None,
+           stride: Union[int, List[int], Tuple[int, ...]] = 1,
+           dilation: Union[int, Tuple[int, ...]] = 1, transposed: bool = False) -> SparseTensor:
+    """Sparse 3-D convolution with the reference's coordinate / map caching rules
+    (TS/nn/functional/conv.py:122-205)."""
+    kernel_size = make_ntuple(kernel_size, ndim=3)
+    stride = make_ntuple(stride, ndim=3)
+    dilation = make_ntuple(dilation, ndim=3)
+    feats = _amp_half(input.feats)
+    ones = (1, 1, 1)
+
+    if kernel_size == ones and stride == ones and dilation == ones:
+        out_stride, out_coords = input.stride, input.coords
+        out_feats = _DenseConv.apply(feats, weight)
+    elif not transposed:
+        out_stride = tuple(input.stride[a] * stride[a] for a in range(3))
+        if out_stride in input.cmaps:
+            out_coords = input.cmaps[out_stride]
+        elif stride == ones:
+            out_coords = input.coords
+        else:
+            out_coords = spdownsample(input.coords, stride, kernel_size, input.stride)
+        key = (input.stride, kernel_size, stride, dilation)
+        if key not in input.kmaps:
+            input.kmaps[key] = build_kernel_map(input.coords, out_coords, kernel_size, input.stride,
+                                                dilation)
+        out_feats = ConvolutionFunction.apply(feats, weight, input.kmaps[key], False)
+    else:
+        out_stride = tuple(input.stride[a] // stride[a] for a in range(3))
+        out_coords = input.cmaps[out_stride]
+        kmap = input.kmaps[(out_stride, kernel_size, stride, dilation)]
+        out_feats = ConvolutionFunction.apply(feats, weight, kmap, True)
+
+    if bias is not None:
+        out_feats = out_feats + bias.to(out_feats.dtype)
+
+    out = SparseTensor(out_feats, out_coords, out_stride)
+    out.cmaps = input.cmaps
+    out.cmaps.setdefault(out_stride, out_coords)
+    out.kmaps = input.kmaps
+    return out
+
+
+# ----------------------------------------------------------------------- activations
+def relu(input: SparseTensor, inplace: bool = True) -> SparseTensor:
+    return fapply(input, torch.nn.functional.relu, inplace=inplace)
+
+
+def leaky_relu(input: SparseTensor, negative_slope: float = 0.1, inplace: bool = True) -> SparseTensor:
+    return fapply(input, torch.nn.functional.leaky_relu, negative_slope=negative_slope,
+                  inplace=inplace)

@@ -1,0 +1,351 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden fixtures produced
+by the reference and against the CPU oracle on seeded inputs.
+
+Bars (BASELINE.json north_star): integer / index results bit-exact; fp32 activations and
+gradients <= 1e-5 relative (max-norm), fp16 <= 1e-3.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_ops as R
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+FP16_TOL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def ts():
+    import openpcseg_b200.torchsparse as ts_mod
+    assert torch.cuda.is_available()
+    return ts_mod
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+def rel_err(a, b):
+    a = a.detach().float().cpu().numpy().astype(np.float64) if torch.is_tensor(a) else a.astype(np.float64)
+    b = b.detach().float().cpu().numpy().astype(np.float64) if torch.is_tensor(b) else b.astype(np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def eq(t, a):
+    return np.array_equal(t.cpu().numpy(), a)
+
+
+def multi_batch_cloud(seed, n=4000, extent=60, batches=3):
+    rng = np.random.default_rng(seed)
+    out = []
+    for b in range(batches):
+        xy = rng.integers(0, extent, size=(n, 2))
+        z = np.where(rng.random(n) < 0.7, (xy[:, 0] // 5 + xy[:, 1] // 7) % 4, rng.integers(0, 20, n))
+        c = np.unique(np.stack([xy[:, 0], xy[:, 1], z], 1), axis=0)
+        rng.shuffle(c)
+        out.append(np.concatenate([c, np.full((len(c), 1), b)], 1))
+    return np.concatenate(out).astype(np.int32)
+
+
+# ------------------------------------------------------------------------------ hashing
+def test_hash_golden_and_oracle(ts, golden):
+    F = ts.nn.functional
+    g = golden("hash_offsets")
+    assert eq(F.sphash(dev(g["ka_coords"])), g["ka_hash"])
+    assert eq(F.sphash(dev(g["rand_coords"])), g["rand_hash"])
+    for name in ["k3", "k2s4", "k133", "k313", "k311", "k3s8"]:
+        off = dev(g[f"off_{name}"])
+        assert eq(F.sphash(dev(g["rand_coords"]), off), g[f"khash_{name}"])
+    c = multi_batch_cloud(1)
+    c[::7, :3] -= 40                                     # negatives
+    assert eq(F.sphash(dev(c)), R.sphash(c))
+    off = R.get_kernel_offsets(3, 2)
+    assert eq(F.sphash(dev(c), dev(off)), R.sphash(c, off))
+    assert F.sphash(torch.zeros((0, 4), dtype=torch.int32, device="cuda")).shape == (0,)
+
+
+def test_kernel_offsets_match_oracle(ts):
+    from openpcseg_b200.torchsparse.nn.utils import get_kernel_offsets
+    for ks, st, dil in [(3, 1, 1), (2, 2, 1), ((1, 3, 3), 4, 1), ((3, 1, 3), (2, 2, 1), 1), (5, 1, 1),
+                        ((3, 1, 1), 1, 2), (1, 1, 1), (4, 1, 1)]:
+        assert np.array_equal(get_kernel_offsets(ks, st, dil).numpy(), R.get_kernel_offsets(ks, st, dil))
+
+
+def test_hash_query_and_count(ts):
+    F = ts.nn.functional
+    rng = np.random.default_rng(5)
+    refs = rng.integers(0, 1 << 59, size=5000).astype(np.int64)
+    refs[100] = refs[7]                                  # duplicate key: first row wins
+    q = np.concatenate([refs[rng.integers(0, 5000, 3000)], rng.integers(0, 1 << 59, 3000)]).astype(np.int64)
+    q = q.reshape(6, 1000)
+    got = F.sphashquery(dev(q), dev(refs))
+    assert got.shape == (6, 1000) and eq(got, R.sphashquery(q, refs))
+    idx = rng.integers(-1, 50, size=10000).astype(np.int32)
+    assert eq(F.spcount(dev(idx), 50), R.spcount(idx, 50))
+    assert F.sphashquery(torch.zeros(0, dtype=torch.int64, device="cuda"), dev(refs)).numel() == 0
+    none = F.sphashquery(dev(q), torch.zeros(0, dtype=torch.int64, device="cuda"))
+    assert bool((none == -1).all())
+
+
+def test_reference_backend_names(ts):
+    """The pybind-level names of the reference (TS/backend/pybind_cuda.cpp:18-39)."""
+    from openpcseg_b200 import backend as B
+    rng = np.random.default_rng(2)
+    refs = np.unique(rng.integers(0, 1 << 50, 300)).astype(np.int64)
+    q = np.concatenate([refs[:50], np.array([3, 5], np.int64)])
+    idx_target = torch.arange(len(refs), device="cuda")
+    out = B.hash_query_cuda(dev(q), dev(refs), idx_target).cpu().numpy()
+    exp = R.sphashquery(q, refs) + 1
+    assert np.array_equal(out, exp)
+    c = multi_batch_cloud(3, n=500, extent=20, batches=1)
+    assert eq(B.hash_cuda(dev(c)), R.sphash(c))
+
+
+# --------------------------------------------------------------- coordinates and maps
+def test_unique_and_downsample(ts, golden):
+    from openpcseg_b200 import backend as B
+    F = ts.nn.functional
+    rng = np.random.default_rng(11)
+    keys = rng.integers(-(1 << 40), 1 << 59, size=20000).astype(np.int64)
+    keys[5000:10000] = keys[:5000]
+    assert eq(B.unique_sorted_i64(dev(keys)), np.unique(keys))
+    g = golden("downsample")
+    for tag, (st, ks, tst) in {"s2k2": (2, 2, 1), "s2k2_t2": (2, 2, 2), "s2k3": (2, 3, 1),
+                               "s221k3": ((2, 2, 1), 3, 1), "s2k3_t2": (2, 3, 2)}.items():
+        assert eq(F.spdownsample(dev(g[f"{tag}_in"]), st, ks, tst), g[f"{tag}_out"]), tag
+    c = multi_batch_cloud(4)
+    for st, ks, tst in [(2, 2, 1), (2, 3, 1), ((2, 2, 1), 3, 1), (2, 2, 4)]:
+        src = c if tst == 1 else R.spdownsample(R.spdownsample(c, 2, 2, 1), 2, 2, 2)
+        assert eq(F.spdownsample(dev(src), st, ks, tst), R.spdownsample(src, st, ks, tst)), (st, ks, tst)
+
+
+@pytest.mark.parametrize("tag,ks", [("k3", 3), ("k133", (1, 3, 3)), ("k313", (3, 1, 3)), ("k311", (3, 1, 1))])
+def test_kmap_golden_submanifold(ts, golden, tag, ks):
+    F = ts.nn.functional
+    g = golden("conv_maps")
+    c = dev(g["coords"])
+    km = F.build_kernel_map(c, c, ks, (1, 1, 1))
+    nbmaps, nbsizes, sizes = km
+    assert eq(nbmaps, g[f"{tag}_nbmaps"]) and eq(nbsizes, g[f"{tag}_nbsizes"])
+    assert sizes == (c.shape[0], c.shape[0])
+    # symmetric maps: nbr_in[k] == nbr_out[K-1-k]
+    _, nbr_in, _ = __import__("openpcseg_b200").backend.kmap_build(
+        c, c, ts.nn.utils.get_kernel_offsets(ks, 1, 1, "cuda"), True)
+    assert torch.equal(nbr_in, km.nbr_out.flip(0))
+
+
+def test_kmap_multibatch_and_strided(ts, golden):
+    F = ts.nn.functional
+    g = golden("conv_maps")
+    c = dev(g["coords"])
+    for tag, st, ks in [("k2s2", 2, 2), ("k3s2", 2, 3), ("k3s221", (2, 2, 1), 3)]:
+        oc = F.spdownsample(c, st, ks, 1)
+        assert eq(oc, g[f"{tag}_coords"])
+        nbmaps, nbsizes, _ = F.build_kernel_map(c, oc, ks, (1, 1, 1))
+        assert eq(nbmaps, g[f"{tag}_nbmaps"]) and eq(nbsizes, g[f"{tag}_nbsizes"]), tag
+    cm = multi_batch_cloud(6)
+    for ks, in_stride in [(3, 1), (2, 1), ((1, 3, 3), 1)]:
+        oc = cm if ks != 2 else R.spdownsample(cm, 2, 2, 1)
+        nb, ns = R.build_kmap(cm, oc, ks, in_stride)
+        km = F.build_kernel_map(dev(cm), dev(cm) if ks != 2 else dev(oc), ks, (in_stride,) * 3)
+        assert eq(km[0], nb) and eq(km[1], ns)
+        # per-offset injectivity + nbr_in is the inverse of nbr_out
+        no = km.nbr_out.cpu().numpy()
+        for k in range(no.shape[0]):
+            v = no[k][no[k] >= 0]
+            assert len(np.unique(v)) == len(v)
+
+
+# ------------------------------------------------------------------------ convolution
+def _sparse(ts, feats, coords, stride=1):
+    x = ts.SparseTensor(feats, coords, stride)
+    x.cmaps[x.stride] = x.coords
+    return x
+
+
+@pytest.mark.parametrize("tag,ks,stride", [("k3", 3, 1), ("k133", (1, 3, 3), 1), ("k311", (3, 1, 1), 1),
+                                            ("k2s2", 2, 2), ("k3s2", 3, 2), ("k3s221", 3, (2, 2, 1))])
+def test_conv_fp32_golden(ts, golden, tag, ks, stride):
+    F = ts.nn.functional
+    g = golden("conv_maps")
+    x = dev(g["feats"]).requires_grad_(True)
+    w = dev(g[f"{tag}_w"]).requires_grad_(True)
+    y = F.conv3d(_sparse(ts, x, dev(g["coords"])), w, ks, stride=stride)
+    assert eq(y.coords, g[f"{tag}_coords"])
+    assert rel_err(y.feats, g[f"{tag}_out"]) < FP32_TOL
+    y.feats.backward(dev(g[f"{tag}_gout"]))
+    assert rel_err(x.grad, g[f"{tag}_gin"]) < FP32_TOL
+    assert rel_err(w.grad, g[f"{tag}_gw"]) < FP32_TOL
+
+
+def test_conv_transposed_and_level2_golden(ts, golden):
+    F = ts.nn.functional
+    g = golden("conv_maps")
+    x0 = _sparse(ts, dev(g["feats"]), dev(g["coords"]))
+    x1 = F.conv3d(x0, dev(g["k2s2_w"]), 2, stride=2)
+    assert rel_err(x1.feats, g["k2s2_out"]) < FP32_TOL
+    # k3 at stride 2 reuses cmaps[(2,2,2)]
+    x1i = ts.SparseTensor(dev(g["k2s2_out"]).requires_grad_(True), x1.coords, x1.stride)
+    x1i.cmaps, x1i.kmaps = x1.cmaps, x1.kmaps
+    w = dev(g["s2k3_w"]).requires_grad_(True)
+    y = F.conv3d(x1i, w, 3)
+    assert rel_err(y.feats, g["s2k3_out"]) < FP32_TOL
+    nbmaps, nbsizes, _ = x1.kmaps[((2, 2, 2), (3, 3, 3), (1, 1, 1), (1, 1, 1))]
+    assert eq(nbmaps, g["s2k3_nbmaps"]) and eq(nbsizes, g["s2k3_nbsizes"])
+    y.feats.backward(dev(g["s2k3_gout"]))
+    assert rel_err(x1i.feats.grad, g["s2k3_gin"]) < FP32_TOL and rel_err(w.grad, g["s2k3_gw"]) < FP32_TOL
+    # transposed k2s2 back to the stride-1 coordinates
+    xt = ts.SparseTensor(dev(g["k2s2_out"]).requires_grad_(True), x1.coords, x1.stride)
+    xt.cmaps, xt.kmaps = x1.cmaps, x1.kmaps
+    wt = dev(g["k2s2t_w"]).requires_grad_(True)
+    yt = F.conv3d(xt, wt, 2, stride=2, transposed=True)
+    assert eq(yt.coords, g["coords"]) and yt.stride == (1, 1, 1)
+    assert rel_err(yt.feats, g["k2s2t_out"]) < FP32_TOL
+    yt.feats.backward(dev(g["k2s2t_gout"]))
+    assert rel_err(xt.feats.grad, g["k2s2t_gin"]) < FP32_TOL and rel_err(wt.grad, g["k2s2t_gw"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("cin,cout", [(4, 32), (32, 32), (64, 96), (96, 96), (128, 128), (192, 128), (20, 20)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_conv_vs_oracle_channels(ts, cin, cout, dtype):
+    """Submanifold k3 + strided k2s2 + transposed, multi-batch, channel shapes of MinkUNet."""
+    F = ts.nn.functional
+    tol = FP32_TOL if dtype == torch.float32 else FP16_TOL
+    c = multi_batch_cloud(21, n=1500, extent=30, batches=2)
+    rng = np.random.default_rng(cin * 131 + cout)
+    x = rng.standard_normal((c.shape[0], cin)).astype(np.float32)
+    w = (rng.standard_normal((27, cin, cout)) / np.sqrt(27 * cin)).astype(np.float32)
+    if dtype == torch.float16:                           # compare on the fp16-rounded operands
+        x = x.astype(np.float16).astype(np.float32)
+        w = w.astype(np.float16).astype(np.float32)
+    nb, ns = R.build_kmap(c, c, 3)
+    go = rng.standard_normal((c.shape[0], cout)).astype(np.float32)
+    if dtype == torch.float16:
+        go = go.astype(np.float16).astype(np.float32)
+    exp = R.conv_forward(x, w, nb, ns, (len(c), len(c)))
+    egi, egw = R.conv_backward(x, w, go, nb, ns)
+    xt = dev(x, dtype).requires_grad_(True)
+    wt = dev(w).requires_grad_(True)                      # fp32 master weights
+    with torch.autocast("cuda", dtype=torch.float16, enabled=dtype == torch.float16):
+        y = F.conv3d(_sparse(ts, xt, dev(c)), wt, 3)
+    assert y.feats.dtype == dtype
+    assert rel_err(y.feats, exp) < tol
+    y.feats.backward(dev(go, dtype))
+    assert rel_err(xt.grad, egi) < tol
+    assert wt.grad.dtype == torch.float32 and rel_err(wt.grad, egw) < tol
+
+
+def test_conv_1x1_bias_and_errors(ts):
+    F = ts.nn.functional
+    c = multi_batch_cloud(8, n=600, extent=20, batches=2)
+    x = torch.randn(len(c), 24, device="cuda", requires_grad=True)
+    w = torch.randn(24, 40, device="cuda", requires_grad=True)
+    b = torch.randn(40, device="cuda")
+    y = F.conv3d(_sparse(ts, x, dev(c)), w, 1, bias=b)
+    ref = x.detach() @ w.detach() + b
+    assert rel_err(y.feats, ref) < FP32_TOL
+    go = torch.randn_like(y.feats)
+    y.feats.backward(go)
+    assert rel_err(x.grad, go @ w.detach().t()) < FP32_TOL
+    assert rel_err(w.grad, x.detach().t() @ go) < FP32_TOL
+    with pytest.raises(ValueError):                       # channel mismatch, like the reference
+        F.conv3d(_sparse(ts, torch.randn(len(c), 5, device="cuda"), dev(c)), torch.randn(27, 6, 8, device="cuda"), 3)
+    # empty tensor
+    e = _sparse(ts, torch.zeros(0, 8, device="cuda"), torch.zeros(0, 4, dtype=torch.int32, device="cuda"))
+    assert F.conv3d(e, torch.randn(27, 8, 8, device="cuda"), 3).feats.shape == (0, 8)
+
+
+def test_module_surface(ts):
+    spnn = ts.nn
+    c = multi_batch_cloud(9, n=800, extent=24, batches=2)
+    net = torch.nn.Sequential(spnn.Conv3d(4, 16, 3), spnn.BatchNorm(16), spnn.ReLU(True),
+                              spnn.Conv3d(16, 16, 2, stride=2), spnn.BatchNorm(16), spnn.ReLU(True),
+                              spnn.Conv3d(16, 8, 2, stride=2, transposed=True)).cuda()
+    x = _sparse(ts, torch.randn(len(c), 4, device="cuda"), dev(c))
+    y = net(x)
+    assert y.feats.shape == (len(c), 8) and y.stride == (1, 1, 1)
+    y.feats.square().mean().backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in net.parameters())
+    z = ts.cat([y, x])
+    assert z.feats.shape[1] == 12 and z.kmaps is x.kmaps
+
+
+# -------------------------------------------------------------------- point <-> voxel
+def test_point_voxel_golden(ts, golden):
+    from openpcseg_b200 import backend as B
+    F = ts.nn.functional
+    g = golden("point_voxel")
+    idx = dev(g["p2v2_idx"]).int()
+    cnt = dev(g["p2v2_counts"])
+    assert rel_err(F.spvoxelize(dev(g["pt_feats"]), idx, cnt), g["p2v2_out"]) < FP32_TOL
+    assert rel_err(B.voxelize_backward(dev(g["vox_bwd_gout"]), idx, cnt, g["pts"].shape[0]),
+                   g["vox_bwd_gin"]) < FP32_TOL
+    for lvl, vc, vf in [("1", g["iv_coords"], g["v2p1_vfeats"]), ("2", g["s2_coords"], g["s2_feats"])]:
+        nfc = R.initial_voxelize(g["pts"], g["pt_feats"], 0.05, 0.05)[4]
+        ii, ww = B.trilinear_map(dev(nfc), dev(vc), int(lvl))
+        assert eq(ii, g[f"v2p{lvl}_idx"]) and rel_err(ww, g[f"v2p{lvl}_w"]) < FP32_TOL
+        out = F.spdevoxelize(dev(vf), ii, ww)
+        assert rel_err(out, g[f"v2p{lvl}_out"]) < FP32_TOL
+        # calc_ti_weights in the reference layout
+        w8 = F.calc_ti_weights(dev(nfc), dev(g[f"v2p{lvl}_idx"]).t().contiguous(), scale=int(lvl))
+        assert rel_err(w8.t(), g[f"v2p{lvl}_w"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("c", [4, 32, 96, 10])
+def test_voxelize_devoxelize_vs_oracle(ts, dtype, c):
+    F = ts.nn.functional
+    tol = FP32_TOL if dtype == torch.float32 else FP16_TOL
+    rng = np.random.default_rng(c)
+    n_pts, n_vox = 5000, 700
+    idx = rng.integers(-1, n_vox, size=n_pts).astype(np.int32)
+    cnt = R.spcount(idx, n_vox)
+    f = rng.standard_normal((n_pts, c)).astype(np.float32)
+    if dtype == torch.float16:
+        f = f.astype(np.float16).astype(np.float32)
+    ft = dev(f, dtype).requires_grad_(True)
+    out = F.spvoxelize(ft, dev(idx), dev(cnt))
+    assert out.dtype == dtype and rel_err(out, R.spvoxelize_forward(f, idx, cnt)) < tol
+    g = rng.standard_normal((n_vox, c)).astype(np.float32)
+    if dtype == torch.float16:
+        g = g.astype(np.float16).astype(np.float32)
+    out.backward(dev(g, dtype))
+    assert rel_err(ft.grad, R.spvoxelize_backward(g, idx, cnt, n_pts)) < tol
+    # devoxelize
+    i8 = rng.integers(-1, n_vox, size=(n_pts, 8)).astype(np.int32)
+    w8 = rng.random((n_pts, 8)).astype(np.float32)
+    vf = rng.standard_normal((n_vox, c)).astype(np.float32)
+    gp = rng.standard_normal((n_pts, c)).astype(np.float32)
+    if dtype == torch.float16:
+        vf = vf.astype(np.float16).astype(np.float32)
+        gp = gp.astype(np.float16).astype(np.float32)
+    vt = dev(vf, dtype).requires_grad_(True)
+    o = F.spdevoxelize(vt, dev(i8), dev(w8))
+    assert rel_err(o, R.spdevoxelize_forward(vf, i8, w8)) < tol
+    o.backward(dev(gp, dtype))
+    assert rel_err(vt.grad, R.spdevoxelize_backward(gp, i8, w8, n_vox)) < tol
+
+
+def test_range_image_ops():
+    from openpcseg_b200 import backend as B
+    rng = np.random.default_rng(0)
+    n, c, b, h, w = 3000, 6, 2, 8, 32
+    pxpy = np.stack([rng.integers(0, b, n), rng.integers(0, w, n), rng.integers(0, h, n)], 1).astype(np.int32)
+    feats = rng.standard_normal((n, c)).astype(np.float32)
+    cm = B.map_count(dev(pxpy), b, h, w)
+    exp_cm = np.zeros((b, 1, h, w), np.int32)
+    np.add.at(exp_cm, (pxpy[:, 0], 0, pxpy[:, 2], pxpy[:, 1]), 1)
+    assert eq(cm, exp_cm)
+    dense = B.denselize_forward(dev(feats), cm, dev(pxpy))
+    exp = np.zeros((b, c, h, w), np.float64)
+    for j in range(c):
+        np.add.at(exp, (pxpy[:, 0], j, pxpy[:, 2], pxpy[:, 1]),
+                  feats[:, j] / exp_cm[pxpy[:, 0], 0, pxpy[:, 2], pxpy[:, 1]])
+    assert rel_err(dense, exp) < FP32_TOL
+    gd = rng.standard_normal((b, c, h, w)).astype(np.float32)
+    gf = B.denselize_backward(dev(gd), cm, dev(pxpy))
+    exp_g = gd[pxpy[:, 0], :, pxpy[:, 2], pxpy[:, 1]] / exp_cm[pxpy[:, 0], 0, pxpy[:, 2], pxpy[:, 1]][:, None]
+    assert rel_err(gf, exp_g) < FP32_TOL
