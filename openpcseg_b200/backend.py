@@ -15,9 +15,45 @@ from typing import Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import check
+from ._lib import check as _check
 
 F32, F16 = 0, 1
+
+# ---- measurement hooks (bench.py): count of libb2s kernel launches and optional per-call
+# CUDA-event timing of the convolution kernels.  Off the hot path unless PROFILER is set.
+STATS = {"launches": 0}
+PROFILER = None          # object with .record(kind, meta, start_event, end_event)
+
+
+def _launched(n: int = 1) -> None:
+    STATS["launches"] += n
+
+
+class _Timed:
+    """Brackets one kernel launch with CUDA events on the current stream when profiling."""
+
+    __slots__ = ("kind", "meta", "start")
+
+    def __init__(self, kind: str, meta: dict):
+        self.kind, self.meta, self.start = kind, meta, None
+
+    def __enter__(self):
+        if PROFILER is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.start is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            PROFILER.record(self.kind, self.meta, self.start, end)
+        return False
+
+
+def check(rc: int, what: str = "", launches: int = 1) -> None:
+    _check(rc, what)
+    STATS["launches"] += launches
 
 
 def _dtype_code(t: torch.Tensor) -> int:
@@ -208,7 +244,7 @@ def kmap_pairs(nbr_out: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 # --------------------------------------------------------------------- convolution
 def conv_gather_gemm(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Tensor],
                      n_rows: int, transpose_w: bool, flip_k: bool,
-                     bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     bias: Optional[torch.Tensor] = None, pairs_hint=None) -> torch.Tensor:
     """out[r] = sum_k feats[nbr[k'][r]] @ (W[k] or W[k]^T); see b2s_conv_gather_gemm."""
     _cuda(feats, weight, nbr, bias)
     feats, weight = feats.contiguous(), weight.contiguous()
@@ -225,28 +261,34 @@ def conv_gather_gemm(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[to
     if bias is not None:
         bias = bias.to(feats.dtype).contiguous()
     out = torch.empty((n_rows, c_res), dtype=feats.dtype, device=feats.device)
+    if n_rows == 0:
+        return out
     L = _lib.lib()
     code = _dtype_code(feats)
     nbytes = L.b2s_conv_workspace_bytes(code, n_rows, c_in, c_out, k)
     ws = _ws(nbytes, feats.device) if nbytes else None
-    check(L.b2s_conv_gather_gemm(code, feats.data_ptr(), feats.shape[0], weight.data_ptr(), k, c_in,
-                                 c_out, int(transpose_w), int(flip_k), _ptr(nbr), n_rows, _ptr(bias),
-                                 out.data_ptr(), _ptr(ws), nbytes, _stream()), "conv_gather_gemm")
+    with _Timed("dgrad" if transpose_w else "fwd",
+                {"k": k, "c_in": c_in, "c_out": c_out, "rows": n_rows, "dtype": code, "pairs": pairs_hint}):
+        check(L.b2s_conv_gather_gemm(code, feats.data_ptr(), feats.shape[0], weight.data_ptr(), k, c_in,
+                                     c_out, int(transpose_w), int(flip_k), _ptr(nbr), n_rows, _ptr(bias),
+                                     out.data_ptr(), _ptr(ws), nbytes, _stream()), "conv_gather_gemm")
     return out
 
 
 def conv_wgrad(feats: torch.Tensor, grad_out: torch.Tensor, k: int, pairs: Optional[torch.Tensor],
-               nbsizes: Optional[torch.Tensor], swap_pairs: bool) -> torch.Tensor:
+               nbsizes: Optional[torch.Tensor], swap_pairs: bool, pairs_hint=None) -> torch.Tensor:
     """fp32 grad_w [K, C_in, C_out]; pairs/nbsizes stay on the device (no sync)."""
     _cuda(feats, grad_out, pairs, nbsizes)
     feats, grad_out = feats.contiguous(), grad_out.contiguous()
     assert feats.dtype == grad_out.dtype
     c_in, c_out = feats.shape[1], grad_out.shape[1]
     gw = torch.empty((k, c_in, c_out), dtype=torch.float32, device=feats.device)
-    check(_lib.lib().b2s_conv_wgrad(_dtype_code(feats), feats.data_ptr(), feats.shape[0],
-                                    grad_out.data_ptr(), grad_out.shape[0], k, c_in, c_out,
-                                    _ptr(pairs), _ptr(nbsizes), int(swap_pairs), gw.data_ptr(), None,
-                                    0, _stream()), "conv_wgrad")
+    with _Timed("wgrad", {"k": k, "c_in": c_in, "c_out": c_out, "rows": feats.shape[0],
+                          "dtype": _dtype_code(feats), "pairs": pairs_hint}):
+        check(_lib.lib().b2s_conv_wgrad(_dtype_code(feats), feats.data_ptr(), feats.shape[0],
+                                        grad_out.data_ptr(), grad_out.shape[0], k, c_in, c_out,
+                                        _ptr(pairs), _ptr(nbsizes), int(swap_pairs), gw.data_ptr(), None,
+                                        0, _stream()), "conv_wgrad")
     return gw
 
 

@@ -53,11 +53,11 @@ int b2s_conv_gather_gemm(int32_t dtype, const void* in, int64_t n_src, const voi
   B2S_REQUIRE(dtype == B2S_F32 || dtype == B2S_F16, B2S_ERR_INVALID, "b2s_conv_gather_gemm: dtype");
   B2S_REQUIRE(k >= 1 && c_in >= 1 && c_out >= 1 && n_rows >= 0 && n_src >= 0, B2S_ERR_INVALID,
               "b2s_conv_gather_gemm: bad sizes");
+  if (n_rows == 0) return B2S_OK;
   B2S_REQUIRE(nbr || k == 1, B2S_ERR_INVALID,
               "b2s_conv_gather_gemm: nbr == NULL (identity map) needs k == 1");
   B2S_REQUIRE(nbr || n_rows <= n_src, B2S_ERR_INVALID,
               "b2s_conv_gather_gemm: identity map with n_rows > n_src");
-  if (n_rows == 0) return B2S_OK;
   B2S_REQUIRE(in && weight && out, B2S_ERR_INVALID, "b2s_conv_gather_gemm: null pointer");
   B2S_REQUIRE(n_rows < (1LL << 31) && n_src < (1LL << 31), B2S_ERR_UNSUPPORTED,
               "b2s_conv_gather_gemm: more than 2^31 rows");

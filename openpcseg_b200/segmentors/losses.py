@@ -1,0 +1,47 @@
+"""Segmentation loss of the voxel segmentors: cross-entropy + Lovasz-softmax
+(pcseg/loss/__init__.py:15-137 defaults, tools/utils/common/lovasz_losses.py:158-205).
+
+The Lovasz term is computed for all classes in one batched sort and without any host
+synchronisation: ignored points get zero error and zero weight instead of being filtered
+out (same value: a zero-error, zero-weight entry changes no cumulative sum), and the
+'present classes only' average is a masked mean.
+"""
+import torch
+from torch import nn
+import torch.nn.functional as TF
+
+__all__ = ["SegLoss", "lovasz_softmax_flat"]
+
+
+def lovasz_softmax_flat(probs: torch.Tensor, labels: torch.Tensor, ignore_index: int) -> torch.Tensor:
+    p_cnt, n_cls = probs.shape
+    valid = (labels != ignore_index)
+    fg = TF.one_hot(labels.clamp(0, n_cls - 1), n_cls).to(probs.dtype) * valid[:, None]   # [P, C]
+    errors = (fg - probs).abs() * valid[:, None]
+    errors_sorted, perm = torch.sort(errors, dim=0, descending=True)
+    fg_sorted = torch.gather(fg, 0, perm)
+    bg_sorted = torch.gather((1.0 - fg) * valid[:, None], 0, perm)
+    gts = fg_sorted.sum(0, keepdim=True)
+    inter = gts - fg_sorted.cumsum(0)
+    union = gts + bg_sorted.cumsum(0)
+    jaccard = 1.0 - inter / union.clamp_min(1e-12)
+    grad = torch.cat([jaccard[:1], jaccard[1:] - jaccard[:-1]], 0)
+    per_class = (errors_sorted * grad).sum(0)
+    present = (gts.squeeze(0) > 0).to(probs.dtype)
+    return (per_class * present).sum() / present.sum().clamp_min(1.0)
+
+
+class SegLoss(nn.Module):
+    def __init__(self, ignore_index: int = 0, label_smoothing: float = 0.0, ce_weight: float = 1.0,
+                 lovasz_weight: float = 1.0):
+        super().__init__()
+        self.ignore_index = ignore_index
+        self.ce = nn.CrossEntropyLoss(ignore_index=ignore_index, label_smoothing=label_smoothing)
+        self.ce_weight, self.lovasz_weight = ce_weight, lovasz_weight
+
+    def forward(self, logits: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        logits = logits.float()
+        loss = self.ce_weight * self.ce(logits, target)
+        loss = loss + self.lovasz_weight * lovasz_softmax_flat(logits.softmax(dim=1), target,
+                                                               self.ignore_index)
+        return loss

@@ -132,6 +132,10 @@ class KernelMap:
             self._pairs = B.kmap_pairs(self.nbr_out)
         return self._pairs
 
+    def total_hint(self):
+        """Device scalar with the pair count M (used by the measurement hooks only)."""
+        return self.pairs()[1] if B.PROFILER is not None else None
+
     def in_gather_map(self) -> Tuple[torch.Tensor, bool]:
         """(map [K, N_in], flip_k) giving, per input row, the output row it feeds."""
         if self.symmetric:
@@ -179,11 +183,12 @@ class ConvolutionFunction(Function):
     def forward(ctx, feats, weight, kmap: KernelMap, transposed: bool):
         feats = feats.contiguous()
         w = weight.to(feats.dtype)
+        hint = kmap.total_hint()
         if not transposed:
-            out = B.conv_gather_gemm(feats, w, kmap.nbr_out, kmap.sizes[1], False, False)
+            out = B.conv_gather_gemm(feats, w, kmap.nbr_out, kmap.sizes[1], False, False, pairs_hint=hint)
         else:
             gmap, flip = kmap.in_gather_map()
-            out = B.conv_gather_gemm(feats, w, gmap, kmap.sizes[0], False, flip)
+            out = B.conv_gather_gemm(feats, w, gmap, kmap.sizes[0], False, flip, pairs_hint=hint)
         ctx.save_for_backward(feats, weight)
         ctx.kmap, ctx.transposed = kmap, transposed
         return out
@@ -196,15 +201,18 @@ class ConvolutionFunction(Function):
         grad_out = grad_out.contiguous()
         w = weight.to(feats.dtype)
         grad_in = grad_w = None
+        hint = kmap.total_hint()
         if ctx.needs_input_grad[0]:
             if not transposed:
                 gmap, flip = kmap.in_gather_map()
-                grad_in = B.conv_gather_gemm(grad_out, w, gmap, kmap.sizes[0], True, flip)
+                grad_in = B.conv_gather_gemm(grad_out, w, gmap, kmap.sizes[0], True, flip, pairs_hint=hint)
             else:
-                grad_in = B.conv_gather_gemm(grad_out, w, kmap.nbr_out, kmap.sizes[1], True, False)
+                grad_in = B.conv_gather_gemm(grad_out, w, kmap.nbr_out, kmap.sizes[1], True, False,
+                                             pairs_hint=hint)
         if ctx.needs_input_grad[1]:
             pairs, _ = kmap.pairs()
-            grad_w = B.conv_wgrad(feats, grad_out, kmap.kvol, pairs, kmap.nbsizes32, transposed)
+            grad_w = B.conv_wgrad(feats, grad_out, kmap.kvol, pairs, kmap.nbsizes32, transposed,
+                                  pairs_hint=hint)
             grad_w = grad_w.to(weight.dtype)
         return grad_in, grad_w, None, None
 

@@ -1,0 +1,91 @@
+"""End-to-end parity of the CUDA MinkUNet against the CPU path built on the reference's
+own CPU backend (oracle/cpu_minkunet.py), same weights, same scan."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _small_batch(seeds, n_azimuth=120):
+    from openpcseg_b200.synthetic import make_batch
+    return make_batch(seeds, n_azimuth=n_azimuth)
+
+
+def test_point_voxel_glue_matches_oracle():
+    from oracle import ref_ops as R
+    import openpcseg_b200.torchsparse as ts
+    from openpcseg_b200.segmentors import initial_voxelize, point_to_voxel, voxel_to_point
+    b = _small_batch([3, 4])
+    coords, feats = torch.from_numpy(b["coords"]).cuda(), torch.from_numpy(b["feats"]).cuda()
+    z = ts.PointTensor(feats, coords.float())
+    x0 = initial_voxelize(z, 0.05, 0.05)
+    vc, vf, idx, cnt, nfc = R.initial_voxelize(b["coords"].astype(np.float32), b["feats"], 0.05, 0.05)
+    assert np.array_equal(x0.C.cpu().numpy(), vc)
+    assert np.array_equal(z.additional_features["idx_query"][1].cpu().numpy(), idx)
+    assert np.array_equal(z.additional_features["counts"][1].cpu().numpy(), cnt)
+    assert np.abs(x0.F.cpu().numpy() - vf).max() <= 1e-5 * np.abs(vf).max()
+    z0 = voxel_to_point(x0, z)
+    i1, w1 = R.trilinear_map(nfc, vc, 1)
+    assert np.array_equal(z.idx_query[(1, 1, 1)].cpu().numpy(), i1)
+    assert np.abs(z.weights[(1, 1, 1)].cpu().numpy() - w1).max() < 1e-6
+    assert z0.idx_query is z.idx_query
+    # stride-2 level through a real strided conv, then point_to_voxel / voxel_to_point there
+    x1 = ts.nn.functional.conv3d(x0, torch.randn(8, 4, 4, device="cuda"), 2, stride=2)
+    oc = R.spdownsample(vc, 2, 2, 1)
+    assert np.array_equal(x1.C.cpu().numpy(), oc)
+    pi, pc = R.point_to_voxel_map(nfc, oc, 2)
+    xv = point_to_voxel(x1, z)
+    assert np.array_equal(z.additional_features["idx_query"][(2, 2, 2)].cpu().numpy(), pi)
+    assert np.array_equal(z.additional_features["counts"][(2, 2, 2)].cpu().numpy(), pc)
+    exp = R.spvoxelize_forward(b["feats"], pi, pc)
+    assert np.abs(xv.F.cpu().numpy() - exp).max() <= 1e-5 * np.abs(exp).max()
+    voxel_to_point(x1, z0)
+    i2, w2 = R.trilinear_map(nfc, oc, 2)
+    assert np.array_equal(z.idx_query[(2, 2, 2)].cpu().numpy(), i2)
+    assert np.abs(z.weights[(2, 2, 2)].cpu().numpy() - w2).max() < 1e-6
+
+
+def test_minkunet_fp32_matches_cpu_reference_path():
+    import openpcseg_b200.torchsparse as ts
+    from openpcseg_b200.segmentors import MinkUNet, minkunet34_config
+    from oracle.cpu_minkunet import CpuMinkUNet
+    torch.manual_seed(1)
+    # a narrow MinkUNet (cr 0.5, one block per stage) keeps the CPU side to seconds
+    cfg = minkunet34_config(cr=0.5, num_layer=(1, 1, 1, 1, 1, 1, 1, 1))
+    model = MinkUNet(cfg).cuda().train()
+    b = _small_batch([7, 8])
+    coords, feats, labels = (torch.from_numpy(b[k]) for k in ("coords", "feats", "labels"))
+    out = model({"lidar": ts.SparseTensor(feats.cuda(), coords.cuda(), 1), "targets": labels.cuda()})
+    out["loss"].backward()
+    cpu = CpuMinkUNet(model.state_dict(), num_layer=cfg.num_layer)
+    logits, loss = cpu.forward(coords, feats, labels)
+    loss.backward()
+    a, e = out["logits"].detach().cpu().numpy(), logits.detach().numpy()
+    assert np.abs(a - e).max() <= 2e-4 * np.abs(e).max(), np.abs(a - e).max() / np.abs(e).max()
+    assert abs(float(out["loss"]) - float(loss)) <= 1e-4 * abs(float(loss))
+    grads = cpu.grads()
+    named = dict(model.named_parameters())
+    worst = 0.0
+    for name in ["stem.0.kernel", "stage1.0.net.0.kernel", "stage2.1.net.3.kernel", "stage4.1.net.0.kernel",
+                 "up1.0.net.0.kernel", "up2.1.0.downsample.0.kernel", "up4.1.0.net.3.kernel",
+                 "classifier.0.weight"]:
+        g, r = named[name].grad.cpu().numpy(), grads[name].numpy()
+        worst = max(worst, np.abs(g - r).max() / max(np.abs(r).max(), 1e-12))
+    assert worst < 5e-3, worst
+
+
+def test_minkunet34_amp_step_runs_and_is_finite():
+    import openpcseg_b200.torchsparse as ts
+    from openpcseg_b200.segmentors import MinkUNet, minkunet34_config
+    torch.manual_seed(0)
+    model = MinkUNet(minkunet34_config()).cuda().train()
+    b = _small_batch([1, 2], n_azimuth=300)
+    lidar = ts.SparseTensor(torch.from_numpy(b["feats"]).cuda(), torch.from_numpy(b["coords"]).cuda(), 1)
+    with torch.autocast("cuda", dtype=torch.float16):
+        out = model({"lidar": lidar, "targets": torch.from_numpy(b["labels"]).cuda()})
+    assert out["logits"].shape == (b["coords"].shape[0], 20)
+    out["loss"].backward()
+    assert torch.isfinite(out["loss"])
+    assert all(torch.isfinite(p.grad).all() for p in model.parameters() if p.grad is not None)
+    assert sum(p.grad is not None for p in model.parameters()) == len(list(model.parameters()))
