@@ -67,8 +67,11 @@ def cpu_reference_run(budget_s: float, steps: int, warmup: int, full_voxels: int
     from oracle.cpu_minkunet import CpuMinkUNet, kind
     from openpcseg_b200.segmentors import MinkUNet, minkunet34_config
     from openpcseg_b200.synthetic import make_batch
-    cores = os.cpu_count() or 1
+    # all host cores up to 64: the reference's OpenMP gather loops and MKL GEMMs on these
+    # small per-offset problems stop scaling (and oversubscribe) well before that
+    cores = min(os.cpu_count() or 1, 64)
     torch.set_num_threads(cores)
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     torch.manual_seed(0)
     state = MinkUNet(minkunet34_config()).state_dict()
     if full_voxels is None:

@@ -63,7 +63,9 @@ int b2s_conv_gather_gemm(int32_t dtype, const void* in, int64_t n_src, const voi
               "b2s_conv_gather_gemm: more than 2^31 rows");
   cudaStream_t st = as_stream(stream);
   const int c_red = transpose_w ? c_out : c_in, c_res = transpose_w ? c_in : c_out;
-  if (dtype == B2S_F16 && !force_simt() && tc_gather_gemm_supported(c_red, c_res)) {
+  const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(weight) |
+                         reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (dtype == B2S_F16 && !force_simt() && aligned && tc_gather_gemm_supported(c_red, c_res)) {
     int rc = launch_gather_gemm_tc(in, weight, k, c_in, c_out, transpose_w, flip_k, nbr, n_rows,
                                    bias, out, ws, ws_bytes, st);
     if (rc != B2S_OK) return rc;

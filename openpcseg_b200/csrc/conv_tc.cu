@@ -1,19 +1,668 @@
-// Tensor-core (tcgen05) sparse convolution family - placeholder until the UMMA kernels
-// land: reports "unsupported" for every shape so conv_api.cu uses the SIMT family.
+// Sparse convolution, tensor-core kernel family (fp16 in, fp32 accumulate) for sm_100a:
+// tcgen05.mma with the accumulator in TMEM, operands staged in 128B/64B-swizzled shared
+// memory by cp.async (LDGSTS, 16-byte row segments, zero-fill for missing neighbours),
+// mbarrier producer/consumer pipeline, warp-specialised:
+//
+//   warps 0-3  producers: gather the 128 neighbour rows of offset k (A tile) and the
+//              weight slice W_k^T (B tile) into the stage ring; afterwards the same
+//              four warps are the epilogue (TMEM -> registers -> fp16 -> global rows)
+//   warp  4    allocates TMEM, one elected lane issues tcgen05.mma / tcgen05.commit
+//
+// Output-stationary implicit GEMM: one CTA owns 128 output rows and accumulates ALL kernel
+// offsets (k-loop x channel chunks) into one TMEM accumulator [128 lanes x C_res columns];
+// offsets for which no row of the tile has a neighbour are skipped.  One write per output
+// row, fp32 accumulation across offsets, no atomics, deterministic.
+//
+// Roofline: tensor pipe for C >= 128 layers; L2->SM gather bandwidth / LDGSTS
+// issue for narrow layers.  Algorithmic FLOPs = 2 * M * C_in * C_out (M = map pairs);
+// algorithmic bytes = 2*C_red*M (gathered rows) + 2*C_res*N_rows + 4*K*N_rows + 2*K*C_in*C_out.
 #include "common.cuh"
 
 namespace b2s {
-bool tc_gather_gemm_supported(int, int) { return false; }
-size_t tc_gather_gemm_workspace(int, int, int) { return 0; }
-int launch_gather_gemm_tc(const void*, const void*, int, int, int, int, int, const int32_t*, int64_t,
-                          const void*, void*, void*, size_t, cudaStream_t) {
-  set_error("tcgen05 conv family not built");
-  return B2S_ERR_UNSUPPORTED;
+
+namespace tc {
+
+constexpr int kTileM = 128;
+constexpr int kProducerThreads = 128;
+constexpr int kThreads = 160;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-bool tc_wgrad_supported(int, int) { return false; }
-int launch_wgrad_tc(const void*, const void*, const int32_t*, const int32_t*, int64_t, int64_t, int,
-                    int, int, int, float*, cudaStream_t) {
-  set_error("tcgen05 wgrad family not built");
-  return B2S_ERR_UNSUPPORTED;
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+               "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
+               : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major operand, rows of ROWB bytes (128 -> SWIZZLE_128B,
+// 64 -> SWIZZLE_64B), 8-row groups contiguous (SBO = 8 * ROWB).  Field layout: cute
+// UMMA::SmemDescriptor (start>>4 @0, LBO>>4 @16, SBO>>4 @32, version=1 @46, layout @61).
+template <int ROWB>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  constexpr uint64_t layout = ROWB == 128 ? 2 : (ROWB == 64 ? 4 : 6);
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                       // LBO (ignored for swizzled K-major)
+  d |= (uint64_t)((8 * ROWB) >> 4) << 32;       // SBO
+  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+  d |= layout << 61;
+  return d;
+}
+
+// kind::f16 instruction descriptor: D=F32, A=B=F16, both K-major, M=128.
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+}
+
+// byte offset of (row, 16-byte chunk) inside a swizzled K-major tile with ROWB-byte rows
+template <int ROWB>
+__device__ __forceinline__ uint32_t swz(int row, int chunk) {
+  if constexpr (ROWB == 128) return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+  else return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+}
+
+struct Params {
+  const __half* in;     // [n_src, c_red]
+  const __half* wt;     // [K][c_res][c_red]  (K-major B operand)
+  const int32_t* nbr;   // [K][n_rows] or nullptr (identity, K == 1)
+  const __half* bias;   // [c_res] or nullptr
+  __half* out;          // [n_rows, c_res]
+  int64_t n_rows;
+  int kvol, c_red, c_res, flip_k;
+  int stages, tmem_cols;
+};
+
+// BK = channels per stage (64 -> 128-byte rows, 32 -> 64-byte rows)
+template <int BK>
+__global__ void __launch_bounds__(kThreads) gather_gemm_tc_kernel(const Params p) {
+  constexpr int ROWB = BK * 2;
+  constexpr int CH = ROWB / 16;          // 16-byte chunks per row
+  constexpr int RPI = 32 / CH;           // rows covered by one warp-wide cp.async
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem is only 16-byte aligned by contract: align the tile ring to 1024 by hand
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int a_bytes = kTileM * ROWB;
+  const int b_bytes = ((p.c_res + 7) / 8) * 8 * ROWB;
+  const int stage_bytes = a_bytes + b_bytes;                 // multiple of 512; keep 1024-aligned
+  const int stage_stride = (stage_bytes + 1023) & ~1023;
+  __shared__ __align__(8) uint64_t s_full[8];
+  __shared__ __align__(8) uint64_t s_empty[8];
+  __shared__ __align__(8) uint64_t s_acc;
+  __shared__ uint32_t s_tmem;
+  __shared__ uint32_t s_active[8];       // bit k set <=> some row of the tile has neighbour k
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * kTileM;
+  const int S = p.stages;
+
+  if (tid < 8) s_active[tid] = 0;
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(smem_u32(&s_full[s]), kProducerThreads);
+      mbar_init(smem_u32(&s_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&s_acc), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) tmem_alloc(smem_u32(&s_tmem), (uint32_t)p.tmem_cols);
+  __syncthreads();
+  // which offsets does this tile need at all?
+  if (warp < 4) {
+    const int64_t r = row0 + tid;
+    for (int k = 0; k < p.kvol; ++k) {
+      bool have = false;
+      if (r < p.n_rows)
+        have = p.nbr ? (__ldg(p.nbr + (int64_t)(p.flip_k ? p.kvol - 1 - k : k) * p.n_rows + r) >= 0)
+                     : true;
+      unsigned m = __ballot_sync(0xffffffffu, have);
+      if (lane == 0 && m) atomicOr(&s_active[k >> 5], 1u << (k & 31));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = s_tmem;
+  const int chunks = p.c_red / BK;
+  int n_active = 0;
+  for (int w = 0; w < 8; ++w) n_active += __popc(s_active[w]);
+  const int iters = n_active * chunks;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers
+    const int LAG = S >= 3 ? 2 : 1;       // stages in flight before the full-barrier arrive (<= S-1)
+    const int sub = lane / CH, chunk = lane % CH;
+    int it = 0;
+    for (int k = 0; k < p.kvol; ++k) {
+      if (!((s_active[k >> 5] >> (k & 31)) & 1u)) continue;
+      // neighbour row of (this warp's row `lane`) for offset k
+      int32_t my_src = -1;
+      {
+        const int64_t r = row0 + warp * 32 + lane;
+        if (r < p.n_rows)
+          my_src = p.nbr ? __ldg(p.nbr + (int64_t)(p.flip_k ? p.kvol - 1 - k : k) * p.n_rows + r)
+                         : (int32_t)r;
+      }
+      const __half* wk = p.wt + (int64_t)k * p.c_res * p.c_red;
+      for (int c = 0; c < chunks; ++c, ++it) {
+        const int s = it % S;
+        if (it >= S) mbar_wait(smem_u32(&s_empty[s]), ((it / S) - 1) & 1);
+        const uint32_t a_base = smem_base + s * stage_stride;
+        const uint32_t b_base = a_base + a_bytes;
+        const int ch0 = c * BK + chunk * 8;
+        // A: 32 rows per warp, RPI rows per instruction
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+          const int rl = i * RPI + sub;                       // row within this warp's 32
+          const int32_t src = __shfl_sync(0xffffffffu, my_src, rl);
+          const __half* g = src >= 0 ? p.in + (int64_t)src * p.c_red + ch0 : p.in;
+          cp_async16(a_base + swz<ROWB>(warp * 32 + rl, chunk), g, src >= 0 ? 16u : 0u);
+        }
+        // B: c_res rows of W_k^T, spread over the 128 producer threads
+        for (int n = warp * RPI + sub; n < p.c_res; n += 4 * RPI)
+          cp_async16(b_base + swz<ROWB>(n, chunk), wk + (int64_t)n * p.c_red + ch0, 16u);
+        cp_async_commit();
+        if (it >= LAG) {
+          if (LAG == 2) cp_async_wait<2>();
+          else cp_async_wait<1>();
+          fence_proxy_async();
+          mbar_arrive(smem_u32(&s_full[(it - LAG) % S]));
+        }
+      }
+    }
+    // drain: signal the last min(LAG, iters) stages
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int j = (iters > LAG ? iters - LAG : 0); j < iters; ++j) mbar_arrive(smem_u32(&s_full[j % S]));
+
+    // -------------------------------------------------------------------- epilogue
+    if (iters > 0) {
+      mbar_wait(smem_u32(&s_acc), 0);
+      tc_fence_after();
+    }
+    const int64_t r = row0 + warp * 32 + lane;
+    const uint32_t t_lane = tmem_acc + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < p.c_res; c0 += 16) {
+      uint32_t v[16];
+      if (iters > 0) {
+        tmem_ld16(t_lane + (uint32_t)c0, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0u;
+      }
+      if (r < p.n_rows) {
+        __align__(16) __half h[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float f = __uint_as_float(v[j]);
+          if (p.bias) f += __half2float(__ldg(p.bias + c0 + j));
+          h[j] = __float2half_rn(f);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(p.out + r * p.c_res + c0);
+        dst[0] = reinterpret_cast<const uint4*>(h)[0];
+        dst[1] = reinterpret_cast<const uint4*>(h)[1];
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ------------------------------------------------------------------ MMA issuer
+    const int n_half = p.c_res > 256 ? p.c_res / 2 : p.c_res;
+    const uint32_t idesc = make_idesc(n_half);
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % S;
+      mbar_wait(smem_u32(&s_full[s]), (it / S) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_base = smem_base + s * stage_stride;
+        const uint32_t b_base = a_base + a_bytes;
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          const uint64_t ad = make_desc<ROWB>(a_base + kk * 32);
+          const uint64_t bd = make_desc<ROWB>(b_base + kk * 32);
+          umma_f16(tmem_acc, ad, bd, idesc, (it | kk) ? 1u : 0u);
+          if (n_half != p.c_res) {
+            const uint64_t bd2 = make_desc<ROWB>(b_base + (n_half / 8) * (8 * ROWB) + kk * 32);
+            umma_f16(tmem_acc + (uint32_t)n_half, ad, bd2, idesc, (it | kk) ? 1u : 0u);
+          }
+        }
+        umma_commit(smem_u32(&s_empty[s]));       // frees the stage when the MMAs retire
+        if (it == iters - 1) umma_commit(smem_u32(&s_acc));
+      }
+      __syncwarp();
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, (uint32_t)p.tmem_cols);
+  }
+}
+
+// W [K][c_in][c_out] -> W^T [K][c_out][c_in] (the K-major B operand of the forward pass)
+__global__ void __launch_bounds__(256) transpose_weight_kernel(const __half* __restrict__ w,
+                                                                __half* __restrict__ wt, int c_in,
+                                                                int c_out) {
+  __shared__ __half tile[32][34];
+  const int k = blockIdx.z;
+  const __half* src = w + (int64_t)k * c_in * c_out;
+  __half* dst = wt + (int64_t)k * c_in * c_out;
+  const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;     // x: c_out, y: c_in
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    int ci = y0 + j, co = x0 + tx;
+    tile[j][tx] = (ci < c_in && co < c_out) ? src[(int64_t)ci * c_out + co] : __float2half(0.f);
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    int co = x0 + j, ci = y0 + tx;
+    if (co < c_out && ci < c_in) dst[(int64_t)co * c_in + ci] = tile[tx][j];
+  }
+}
+
+static int tmem_cols_for(int n) {
+  int c = 32;
+  while (c < n) c <<= 1;
+  return c;
+}
+
+}  // namespace tc
+
+bool tc_gather_gemm_supported(int c_red, int c_res) {
+  if (c_red % 32 != 0 || c_red < 32) return false;
+  if (c_res % 16 != 0 || c_res < 16 || c_res > 512) return false;
+  if (c_res > 256 && (c_res / 2) % 16 != 0) return false;
+  return true;
+}
+
+size_t tc_gather_gemm_workspace(int k, int c_in, int c_out) {
+  return align_up((size_t)k * c_in * c_out * sizeof(__half), 256);   // W^T for the forward pass
+}
+
+int launch_gather_gemm_tc(const void* in, const void* weight, int k, int c_in, int c_out,
+                          int transpose_w, int flip_k, const int32_t* nbr, int64_t n_rows,
+                          const void* bias, void* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  using namespace tc;
+  const int c_red = transpose_w ? c_out : c_in, c_res = transpose_w ? c_in : c_out;
+  const __half* wt = reinterpret_cast<const __half*>(weight);
+  if (!transpose_w) {
+    // forward: B_k[n = c_out][c = c_in] = W[k][c][n]  -> needs W^T
+    B2S_REQUIRE(ws && ws_bytes >= tc_gather_gemm_workspace(k, c_in, c_out), B2S_ERR_WORKSPACE,
+                "b2s_conv_gather_gemm: workspace needs %zu bytes",
+                tc_gather_gemm_workspace(k, c_in, c_out));
+    dim3 g((unsigned)ceil_div(c_out, 32), (unsigned)ceil_div(c_in, 32), (unsigned)k);
+    transpose_weight_kernel<<<g, 256, 0, st>>>(wt, reinterpret_cast<__half*>(ws), c_in, c_out);
+    wt = reinterpret_cast<const __half*>(ws);
+  }  // input gradient: B_k[n = c_in][c = c_out] = W[k][n][c] is the stored layout already
+  Params p;
+  p.in = reinterpret_cast<const __half*>(in);
+  p.wt = wt;
+  p.nbr = nbr;
+  p.bias = reinterpret_cast<const __half*>(bias);
+  p.out = reinterpret_cast<__half*>(out);
+  p.n_rows = n_rows;
+  p.kvol = k;
+  p.c_red = c_red;
+  p.c_res = c_res;
+  p.flip_k = flip_k;
+  p.tmem_cols = tmem_cols_for(c_res);
+  const bool bk64 = (c_red % 64 == 0);
+  const int rowb = bk64 ? 128 : 64;
+  const int stage = ((kTileM * rowb + ((c_res + 7) / 8) * 8 * rowb) + 1023) & ~1023;
+  // two CTAs per SM when the ring fits twice (and TMEM allows it), else one deep ring
+  int stages = (110 * 1024) / stage;
+  if (stages < 3 || p.tmem_cols > 256) stages = (220 * 1024) / stage;
+  if (stages > 6) stages = 6;
+  B2S_REQUIRE(stages >= 2, B2S_ERR_UNSUPPORTED, "b2s_conv_gather_gemm: tile does not fit (C=%d)", c_res);
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage + 1024;
+  const unsigned grid = (unsigned)ceil_div(n_rows, kTileM);
+  if (bk64) {
+    cudaFuncSetAttribute(gather_gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+    gather_gemm_tc_kernel<64><<<grid, kThreads, smem, st>>>(p);
+  } else {
+    cudaFuncSetAttribute(gather_gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)smem);
+    gather_gemm_tc_kernel<32><<<grid, kThreads, smem, st>>>(p);
+  }
+  return B2S_OK;
+}
+
+// =====================================================================================
+// Weight gradient on tensor cores:  dW[k] (C_in x C_out) = sum over the pairs (i, o) of
+// offset k of  X[i]^T * dY[o].   The reduction (GEMM-K) dimension is the pair list, so both
+// operands are "MN-major": a gathered row (64 channels = 128 bytes) is one K-row of a
+// SWIZZLE_128B MN-major panel.  The gather code is the one of the forward kernel; only the
+// descriptors differ (a_major = b_major = MN, LBO = panel stride, SBO = 8 K-rows).
+//
+// Work unit = (offset k, run of <= unit_pairs pairs, 128-channel slab of C_in).  Persistent
+// CTAs stride over the units; pair counts come from the device-resident nbsizes (no host
+// sync).  Per unit the accumulator [128 lanes = c_in, C_out columns] lives in TMEM and is
+// added into the fp32 dW with vector reds.
+namespace tcw {
+using namespace tc;
+
+constexpr int kRows = 64;                    // pairs per pipeline stage (4 MMAs of K = 16)
+constexpr int kPanelBytes = kRows * 128;     // one 64-channel panel of one stage
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t panel_stride_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((panel_stride_bytes >> 4) & 0x3FFF) << 16;   // LBO: next 64-channel panel
+  d |= (uint64_t)(1024 >> 4) << 32;                            // SBO: next 8 K-rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                                      // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ uint32_t make_idesc_mn(int n) {
+  return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(kTileM >> 4) << 24);
+}
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
+struct WParams {
+  const __half* x;        // [n_in, c_in]
+  const __half* gy;       // [n_out, c_out]
+  const int32_t* pairs;   // [M, 2] (in, out) or nullptr (identity)
+  const int32_t* nbsizes; // [K] or nullptr
+  float* gw;              // [K, c_in, c_out]
+  int64_t n_identity;
+  int kvol, c_in, c_out, swap_pairs;
+  int m_tiles, unit_pairs, stages, tmem_cols;
+};
+
+__global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int b_panels = (p.c_out + 63) / 64;
+  const int a_bytes = 2 * kPanelBytes;
+  const int stage_stride = a_bytes + b_panels * kPanelBytes;       // multiples of 8 KiB
+  __shared__ __align__(8) uint64_t s_full[8];
+  __shared__ __align__(8) uint64_t s_empty[8];
+  __shared__ __align__(8) uint64_t s_acc;
+  __shared__ uint32_t s_tmem;
+  __shared__ int64_t s_start[130];         // exclusive prefix of nbsizes
+  __shared__ int s_units[130];             // exclusive prefix of units per offset
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = p.stages;
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(smem_u32(&s_full[s]), kProducerThreads);
+      mbar_init(smem_u32(&s_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&s_acc), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    int64_t acc = 0;
+    int u = 0;
+    for (int k = 0; k < p.kvol; ++k) {
+      s_start[k] = acc;
+      s_units[k] = u;
+      int64_t cnt = p.pairs ? (int64_t)__ldg(p.nbsizes + k) : p.n_identity;
+      acc += cnt;
+      u += (int)((cnt + p.unit_pairs - 1) / p.unit_pairs);
+    }
+    s_start[p.kvol] = acc;
+    s_units[p.kvol] = u;
+  }
+  if (warp == 4) tmem_alloc(smem_u32(&s_tmem), (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = s_tmem;
+  const int total_units = s_units[p.kvol] * p.m_tiles;
+  const int n_half = p.c_out > 256 ? p.c_out / 2 : p.c_out;
+
+  int it = 0;            // global stage counter (ring position / phases continue across units)
+  int unit_no = 0;       // units processed by this CTA (phase of s_acc)
+  for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++unit_no) {
+    const int mt = unit % p.m_tiles;
+    const int ku = unit / p.m_tiles;
+    int k = 0;
+    while (s_units[k + 1] <= ku) ++k;
+    const int64_t cnt_k = s_start[k + 1] - s_start[k];
+    const int64_t lo = (int64_t)(ku - s_units[k]) * p.unit_pairs;
+    const int64_t hi = lo + p.unit_pairs < cnt_k ? lo + p.unit_pairs : cnt_k;
+    const int n_stage = (int)((hi - lo + kRows - 1) / kRows);
+    const int ch_base = mt * 128;                                   // first c_in channel of the slab
+
+    if (warp < 4) {
+      // ---------------------------------------------------------------- producers
+      const int LAG = S >= 3 ? 2 : 1;
+      const int sub = lane >> 3, chunk = lane & 7;
+      const int2* pr = reinterpret_cast<const int2*>(p.pairs);
+      for (int st = 0; st < n_stage; ++st, ++it) {
+        const int s = it % S;
+        if (it >= S) mbar_wait(smem_u32(&s_empty[s]), ((it / S) - 1) & 1);
+        const uint32_t a_base = smem_base + s * stage_stride;
+        const uint32_t b_base = a_base + a_bytes;
+        // this warp stages rows [warp*16, warp*16+16) of the 64-pair stage
+        int32_t my_i = -1, my_o = -1;
+        if (lane < 16) {
+          const int64_t q = lo + (int64_t)st * kRows + warp * 16 + lane;
+          if (q < hi) {
+            if (pr) {
+              int2 v = __ldg(pr + s_start[k] + q);
+              my_i = p.swap_pairs ? v.y : v.x;
+              my_o = p.swap_pairs ? v.x : v.y;
+            } else {
+              my_i = my_o = (int32_t)q;
+            }
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int rl = g * 4 + sub;                               // row within the warp's 16
+          const int row = warp * 16 + rl;
+          const int32_t i = __shfl_sync(0xffffffffu, my_i, rl);
+          const int32_t o = __shfl_sync(0xffffffffu, my_o, rl);
+          const uint32_t off = swz<128>(row, chunk);
+          // A: two 64-channel panels of X
+#pragma unroll
+          for (int pn = 0; pn < 2; ++pn) {
+            const int ch = ch_base + pn * 64 + chunk * 8;
+            if (ch < p.c_in)
+              cp_async16(a_base + pn * kPanelBytes + off, i >= 0 ? p.x + (int64_t)i * p.c_in + ch : p.x,
+                         i >= 0 ? 16u : 0u);
+          }
+          // B: all panels of dY
+          for (int pn = 0; pn < b_panels; ++pn) {
+            const int ch = pn * 64 + chunk * 8;
+            if (ch < p.c_out)
+              cp_async16(b_base + pn * kPanelBytes + off,
+                         o >= 0 ? p.gy + (int64_t)o * p.c_out + ch : p.gy, o >= 0 ? 16u : 0u);
+          }
+        }
+        cp_async_commit();
+        if (st >= LAG) {
+          if (LAG == 2) cp_async_wait<2>();
+          else cp_async_wait<1>();
+          fence_proxy_async();
+          mbar_arrive(smem_u32(&s_full[(it - LAG) % S]));
+        }
+      }
+      cp_async_wait<0>();
+      fence_proxy_async();
+      for (int j = (n_stage > LAG ? n_stage - LAG : 0); j < n_stage; ++j)
+        mbar_arrive(smem_u32(&s_full[(it - n_stage + j) % S]));
+
+      // ----------------------------------------------------------------- epilogue
+      mbar_wait(smem_u32(&s_acc), unit_no & 1);
+      tc_fence_after();
+      const int ci = ch_base + warp * 32 + lane;
+      const uint32_t t_lane = tmem_acc + ((uint32_t)(warp * 32) << 16);
+      float* dst = p.gw + ((int64_t)k * p.c_in + ci) * p.c_out;
+      for (int c0 = 0; c0 < p.c_out; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_lane + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (ci < p.c_in) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            red_add_v4(dst + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                       __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        }
+      }
+      tc_fence_before();
+    } else {
+      // --------------------------------------------------------------- MMA issuer
+      const uint32_t idesc = make_idesc_mn(n_half);
+      for (int st = 0; st < n_stage; ++st, ++it) {
+        const int s = it % S;
+        mbar_wait(smem_u32(&s_full[s]), (it / S) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_base = smem_base + s * stage_stride;
+          const uint32_t b_base = a_base + a_bytes;
+#pragma unroll
+          for (int kk = 0; kk < kRows / 16; ++kk) {
+            const uint64_t ad = make_desc_mn(a_base + kk * 2048, kPanelBytes);
+            const uint64_t bd = make_desc_mn(b_base + kk * 2048, kPanelBytes);
+            umma_f16(tmem_acc, ad, bd, idesc, (st | kk) ? 1u : 0u);
+            if (n_half != p.c_out) {
+              const uint64_t bd2 = make_desc_mn(b_base + (n_half / 64) * kPanelBytes + kk * 2048,
+                                                kPanelBytes);
+              umma_f16(tmem_acc + (uint32_t)n_half, ad, bd2, idesc, (st | kk) ? 1u : 0u);
+            }
+          }
+          umma_commit(smem_u32(&s_empty[s]));
+          if (st == n_stage - 1) umma_commit(smem_u32(&s_acc));
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, (uint32_t)p.tmem_cols);
+  }
+}
+
+}  // namespace tcw
+
+bool tc_wgrad_supported(int c_in, int c_out) {
+  if (c_in % 8 != 0 || c_in < 8) return false;
+  if (c_out % 16 != 0 || c_out < 16 || c_out > 512) return false;
+  if (c_out > 256 && ((c_out / 2) % 64 != 0)) return false;   // split needs a panel boundary
+  return true;
+}
+
+int launch_wgrad_tc(const void* in, const void* gout, const int32_t* nbmaps,
+                    const int32_t* nbsizes, int64_t n_identity, int64_t n_pairs_bound, int k,
+                    int c_in, int c_out, int swap_pairs, float* gw, cudaStream_t st) {
+  using namespace tcw;
+  B2S_REQUIRE(k <= 128, B2S_ERR_UNSUPPORTED, "b2s_conv_wgrad: kernel volume %d > 128", k);
+  WParams p;
+  p.x = reinterpret_cast<const __half*>(in);
+  p.gy = reinterpret_cast<const __half*>(gout);
+  p.pairs = nbmaps;
+  p.nbsizes = nbsizes;
+  p.gw = gw;
+  p.n_identity = n_identity;
+  p.kvol = k;
+  p.c_in = c_in;
+  p.c_out = c_out;
+  p.swap_pairs = swap_pairs;
+  p.m_tiles = (c_in + 127) / 128;
+  p.tmem_cols = tc::tmem_cols_for(c_out);
+  const int stage = (2 + (c_out + 63) / 64) * kPanelBytes;
+  int stages = (int)((220 * 1024) / stage);
+  if (stages > 6) stages = 6;
+  B2S_REQUIRE(stages >= 2, B2S_ERR_UNSUPPORTED, "b2s_conv_wgrad: tile does not fit (C_out=%d)", c_out);
+  p.stages = stages;
+  // unit size: enough units to fill the machine ~3x, at least 8 stages per unit
+  // (the true pair count lives on the device; on LiDAR surfaces ~1/4 of the K*N slots exist)
+  const int sms = sm_count();
+  const int64_t est = k > 1 ? n_pairs_bound / 4 + 1 : n_pairs_bound;
+  int64_t per = est / ((int64_t)sms * 3) + 1;
+  int64_t unit = ((per + kRows - 1) / kRows) * kRows;
+  if (unit < 8 * kRows) unit = 8 * kRows;
+  if (unit > 256 * kRows) unit = 256 * kRows;
+  p.unit_pairs = (int)unit;
+  const size_t smem = (size_t)stages * stage + 1024;
+  cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int64_t max_units = (n_pairs_bound / unit + k) * p.m_tiles;
+  int grid = (int)(max_units < sms ? (max_units < 1 ? 1 : max_units) : sms);
+  wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(p);
+  return B2S_OK;
+}
+
 }  // namespace b2s

@@ -349,3 +349,79 @@ def test_range_image_ops():
     gf = B.denselize_backward(dev(gd), cm, dev(pxpy))
     exp_g = gd[pxpy[:, 0], :, pxpy[:, 2], pxpy[:, 1]] / exp_cm[pxpy[:, 0], 0, pxpy[:, 2], pxpy[:, 1]][:, None]
     assert rel_err(gf, exp_g) < FP32_TOL
+
+
+# ---------------------------------------------------- tensor-core family specific cases
+@pytest.mark.parametrize("cin,cout", [(256, 256), (384, 256), (128, 96), (32, 64)])
+def test_tc_conv_wide_channels_fp16(ts, cin, cout):
+    """tcgen05 path: N > 256 split (dgrad of 384->256), 3 m-tiles in wgrad, SW64 rows (C=32/96)."""
+    F = ts.nn.functional
+    c = multi_batch_cloud(31, n=900, extent=26, batches=2)
+    rng = np.random.default_rng(cin + cout)
+    h = lambda a: a.astype(np.float16).astype(np.float32)
+    x = h(rng.standard_normal((len(c), cin)))
+    w = h(rng.standard_normal((27, cin, cout)) / np.sqrt(27 * cin))
+    go = h(rng.standard_normal((len(c), cout)))
+    nb, ns = R.build_kmap(c, c, 3)
+    exp = R.conv_forward(x, w, nb, ns, (len(c), len(c)))
+    egi, egw = R.conv_backward(x, w, go, nb, ns)
+    xt = dev(x, torch.float16).requires_grad_(True)
+    wt = dev(w).requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.float16):
+        y = F.conv3d(_sparse(ts, xt, dev(c)), wt, 3)
+    assert rel_err(y.feats, exp) < FP16_TOL
+    y.feats.backward(dev(go, torch.float16))
+    assert rel_err(xt.grad, egi) < FP16_TOL
+    assert rel_err(wt.grad, egw) < FP16_TOL
+
+
+def test_tc_strided_transposed_dense_fp16(ts):
+    F = ts.nn.functional
+    c = multi_batch_cloud(33, n=1200, extent=28, batches=2)
+    rng = np.random.default_rng(9)
+    h = lambda a: a.astype(np.float16).astype(np.float32)
+    cin, cmid = 64, 96
+    x = h(rng.standard_normal((len(c), cin)))
+    wd = h(rng.standard_normal((8, cin, cmid)) / np.sqrt(8 * cin))
+    wu = h(rng.standard_normal((8, cmid, cin)) / np.sqrt(8 * cmid))
+    w1 = h(rng.standard_normal((cin, 128)) / np.sqrt(cin))
+    oc = R.spdownsample(c, 2, 2, 1)
+    nb, ns = R.build_kmap(c, oc, 2)
+    y1 = R.conv_forward(x, wd, nb, ns, (len(c), len(oc)))
+    y1h = h(y1)
+    y2 = R.conv_forward(y1h, wu, nb, ns, (len(c), len(oc)), transposed=True)
+    xt = dev(x, torch.float16).requires_grad_(True)
+    wdt, wut, w1t = (dev(a).requires_grad_(True) for a in (wd, wu, w1))
+    with torch.autocast("cuda", dtype=torch.float16):
+        s0 = _sparse(ts, xt, dev(c))
+        s1 = F.conv3d(s0, wdt, 2, stride=2)
+        s2 = F.conv3d(s1, wut, 2, stride=2, transposed=True)
+        s3 = F.conv3d(s2, w1t, 1)
+    assert eq(s1.coords, oc)
+    assert rel_err(s1.feats, y1) < FP16_TOL
+    assert rel_err(s2.feats, y2) < 2 * FP16_TOL          # two fp16 roundings deep
+    y3 = h(s2.feats.float().cpu().numpy()) @ w1
+    assert rel_err(s3.feats, y3) < FP16_TOL
+    go = h(rng.standard_normal((len(c), 128)))
+    s3.feats.backward(dev(go, torch.float16))
+    # gradients of the last (dense) layer against numpy on the same fp16 inputs
+    s2n = s2.feats.detach().float().cpu().numpy()
+    assert rel_err(w1t.grad, s2n.T @ go) < FP16_TOL
+    g2 = h(go @ w1.T)
+    egi, egw = R.conv_backward(y1h, wu, g2, nb, ns, transposed=True)
+    assert rel_err(wut.grad, egw) < 2 * FP16_TOL
+    assert torch.isfinite(xt.grad).all() and torch.isfinite(wdt.grad).all()
+
+
+def test_tc_matches_simt_bitwise_maps_and_close_values(ts):
+    """Same inputs through both kernel families (B2S_FORCE_SIMT is read once per process, so
+    the SIMT result comes from the fp32 path on the fp16-rounded operands)."""
+    F = ts.nn.functional
+    c = multi_batch_cloud(35, n=2500, extent=40, batches=3)
+    rng = np.random.default_rng(4)
+    h = lambda a: a.astype(np.float16).astype(np.float32)
+    x, w = h(rng.standard_normal((len(c), 64))), h(rng.standard_normal((27, 64, 64)) / 40)
+    y32 = F.conv3d(_sparse(ts, dev(x), dev(c)), dev(w), 3).feats
+    with torch.autocast("cuda", dtype=torch.float16):
+        y16 = F.conv3d(_sparse(ts, dev(x, torch.float16), dev(c)), dev(w), 3).feats
+    assert rel_err(y16, y32) < FP16_TOL
