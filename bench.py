@@ -67,9 +67,10 @@ def cpu_reference_run(budget_s: float, steps: int, warmup: int, full_voxels: int
     from oracle.cpu_minkunet import CpuMinkUNet, kind
     from openpcseg_b200.segmentors import MinkUNet, minkunet34_config
     from openpcseg_b200.synthetic import make_batch
-    # all host cores up to 64: the reference's OpenMP gather loops and MKL GEMMs on these
-    # small per-offset problems stop scaling (and oversubscribe) well before that
-    cores = min(os.cpu_count() or 1, 64)
+    # Thread count: measured on the 128-core B200 host (scripts/cpu_baseline_probe.py, 1/32
+    # sub-scan): 8 threads 5.1 s, 32 threads 25.4 s - the reference's per-offset OpenMP gather
+    # loops + small MKL GEMMs slow down when oversubscribed, so 8 is the fastest setting.
+    cores = min(os.cpu_count() or 1, int(os.environ.get("B2S_CPU_THREADS", 8)))
     torch.set_num_threads(cores)
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
     torch.manual_seed(0)
@@ -86,8 +87,8 @@ def cpu_reference_run(budget_s: float, steps: int, warmup: int, full_voxels: int
         loss.backward()
         return time.perf_counter() - t0, b["coords"].shape[0]
 
-    # calibrate on a 1/64 sub-scan, then size the sample to the time budget
-    t_cal, v_cal = one(max(FULL_AZIMUTH // 64, 8), 100)
+    # calibrate on a 1/32 sub-scan, then size the sample to the time budget
+    t_cal, v_cal = one(max(FULL_AZIMUTH // 32, 8), 100)
     rate = v_cal / t_cal                                     # voxels per second, first guess
     per_step = budget_s / max(steps + warmup, 1)
     n_az = int(np.clip(FULL_AZIMUTH * (rate * per_step) / full_voxels, 24, FULL_AZIMUTH))

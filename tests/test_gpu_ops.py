@@ -400,7 +400,7 @@ def test_tc_strided_transposed_dense_fp16(ts):
     assert eq(s1.coords, oc)
     assert rel_err(s1.feats, y1) < FP16_TOL
     assert rel_err(s2.feats, y2) < 2 * FP16_TOL          # two fp16 roundings deep
-    y3 = h(s2.feats.float().cpu().numpy()) @ w1
+    y3 = h(s2.feats.detach().float().cpu().numpy()) @ w1
     assert rel_err(s3.feats, y3) < FP16_TOL
     go = h(rng.standard_normal((len(c), 128)))
     s3.feats.backward(dev(go, torch.float16))
