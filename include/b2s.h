@@ -102,14 +102,18 @@ int b2s_downsample_coords(const int32_t* coords, int64_t n, const int32_t* strid
  *   nbr_in  [K, n_in ] int32 : output row fed by input row i through W[k], or -1
  *                              (may be NULL)
  *   nbsizes [K] int32        : pairs per offset
+ *   tile_mask_out / tile_mask_in (optional, may be NULL): uint32 [ceil(n/128)][ceil(K/32)],
+ *                              bit k of tile t set <=> some row of the 128-row tile t of
+ *                              nbr_out / nbr_in has a neighbour for offset k (lets the
+ *                              convolution skip whole (tile, offset) steps without scanning)
  * b2s_kmap_pairs then emits the reference-format pair list: nbmaps int32 [M,2] =
  * (in, out), grouped by k ascending, out ascending inside a group; d_total[0]=M.
  * `nbmaps` must hold K*n_out rows.                                            */
 size_t b2s_kmap_workspace_bytes(int64_t n_in, int64_t n_out, int32_t k);
 int b2s_kmap_build(const int32_t* in_coords, int64_t n_in, const int32_t* out_coords,
                    int64_t n_out, const int32_t* offsets, int32_t k, int32_t* nbr_out,
-                   int32_t* nbr_in, int32_t* nbsizes, void* ws, size_t ws_bytes,
-                   b2s_stream_t stream);
+                   int32_t* nbr_in, int32_t* nbsizes, uint32_t* tile_mask_out,
+                   uint32_t* tile_mask_in, void* ws, size_t ws_bytes, b2s_stream_t stream);
 int b2s_kmap_pairs(const int32_t* nbr_out, int32_t k, int64_t n_out, int32_t* nbmaps,
                    int64_t* d_total, void* ws, size_t ws_bytes, b2s_stream_t stream);
 
@@ -123,7 +127,8 @@ int b2s_kmap_pairs(const int32_t* nbr_out, int32_t k, int64_t n_out, int32_t* nb
  *   (forward: c_red = c_in, c_res = c_out) or weight[k]^T when transpose_w == 1
  *   (input gradient: c_red = c_out, c_res = c_in).  fp32 accumulation over all
  *   offsets, one write per output row, no atomics, deterministic.
- *   `in` has n_src rows of c_red channels; `out` n_rows x c_res; optional bias[c_res].
+ *   `in` has n_src rows of c_red channels; `out` n_rows x c_res; optional bias[c_res];
+ *   optional tile_mask = the b2s_kmap_build mask that belongs to `nbr` (NULL: scanned).
  * b2s_conv_wgrad: grad_w[k] = sum over pairs of offset k of in[i]^T * grad_out[o],
  *   pairs from b2s_kmap_pairs (device-resident sizes, no host sync).  grad_w is
  *   fp32 [K, c_in, c_out] and is zero-filled by the call.
@@ -133,8 +138,9 @@ size_t b2s_conv_workspace_bytes(int32_t dtype, int64_t n_rows, int32_t c_in, int
                                 int32_t k);
 int b2s_conv_gather_gemm(int32_t dtype, const void* in, int64_t n_src, const void* weight,
                          int32_t k, int32_t c_in, int32_t c_out, int32_t transpose_w,
-                         int32_t flip_k, const int32_t* nbr, int64_t n_rows, const void* bias,
-                         void* out, void* ws, size_t ws_bytes, b2s_stream_t stream);
+                         int32_t flip_k, const int32_t* nbr, const uint32_t* tile_mask,
+                         int64_t n_rows, const void* bias, void* out, void* ws, size_t ws_bytes,
+                         b2s_stream_t stream);
 int b2s_conv_wgrad(int32_t dtype, const void* in, int64_t n_in, const void* grad_out,
                    int64_t n_out, int32_t k, int32_t c_in, int32_t c_out, const int32_t* nbmaps,
                    const int32_t* nbsizes, int32_t swap_pairs, float* grad_w, void* ws,

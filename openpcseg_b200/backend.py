@@ -207,8 +207,9 @@ def downsample_coords(coords: torch.Tensor, stride, kernel_size, tensor_stride) 
 
 # ---------------------------------------------------------------------- kernel map
 def kmap_build(in_coords: torch.Tensor, out_coords: torch.Tensor, offsets: torch.Tensor,
-               want_nbr_in: bool) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]:
-    """(nbr_out int32 [K, N_out], nbr_in int32 [K, N_in] | None, nbsizes int32 [K])."""
+               want_nbr_in: bool):
+    """(nbr_out int32 [K, N_out], nbr_in int32 [K, N_in] | None, nbsizes int32 [K],
+    mask_out int32 [tiles_out, words], mask_in | None) - masks: active offsets per 128-row tile."""
     _cuda(in_coords, out_coords, offsets)
     in_coords, out_coords, offsets = in_coords.contiguous(), out_coords.contiguous(), offsets.contiguous()
     assert in_coords.dtype == out_coords.dtype == offsets.dtype == torch.int32
@@ -217,13 +218,18 @@ def kmap_build(in_coords: torch.Tensor, out_coords: torch.Tensor, offsets: torch
     nbr_out = torch.empty((k, n_out), dtype=torch.int32, device=dev)
     nbr_in = torch.empty((k, n_in), dtype=torch.int32, device=dev) if want_nbr_in else None
     nbsizes = torch.empty(k, dtype=torch.int32, device=dev)
+    words = (k + 31) // 32
+    mask_out = torch.empty((max((n_out + 127) // 128, 1), words), dtype=torch.int32, device=dev)
+    mask_in = (torch.empty((max((n_in + 127) // 128, 1), words), dtype=torch.int32, device=dev)
+               if want_nbr_in else None)
     L = _lib.lib()
     nbytes = L.b2s_kmap_workspace_bytes(n_in, n_out, k)
     ws = _ws(nbytes, dev)
     check(L.b2s_kmap_build(in_coords.data_ptr(), n_in, out_coords.data_ptr(), n_out,
                            offsets.data_ptr(), k, nbr_out.data_ptr(), _ptr(nbr_in),
-                           nbsizes.data_ptr(), ws.data_ptr(), nbytes, _stream()), "kmap_build")
-    return nbr_out, nbr_in, nbsizes
+                           nbsizes.data_ptr(), mask_out.data_ptr(), _ptr(mask_in), ws.data_ptr(),
+                           nbytes, _stream()), "kmap_build")
+    return nbr_out, nbr_in, nbsizes, mask_out, mask_in
 
 
 def kmap_pairs(nbr_out: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -244,7 +250,8 @@ def kmap_pairs(nbr_out: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 # --------------------------------------------------------------------- convolution
 def conv_gather_gemm(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Tensor],
                      n_rows: int, transpose_w: bool, flip_k: bool,
-                     bias: Optional[torch.Tensor] = None, pairs_hint=None) -> torch.Tensor:
+                     bias: Optional[torch.Tensor] = None, pairs_hint=None,
+                     tile_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[r] = sum_k feats[nbr[k'][r]] @ (W[k] or W[k]^T); see b2s_conv_gather_gemm."""
     _cuda(feats, weight, nbr, bias)
     feats, weight = feats.contiguous(), weight.contiguous()
@@ -270,8 +277,9 @@ def conv_gather_gemm(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[to
     with _Timed("dgrad" if transpose_w else "fwd",
                 {"k": k, "c_in": c_in, "c_out": c_out, "rows": n_rows, "dtype": code, "pairs": pairs_hint}):
         check(L.b2s_conv_gather_gemm(code, feats.data_ptr(), feats.shape[0], weight.data_ptr(), k, c_in,
-                                     c_out, int(transpose_w), int(flip_k), _ptr(nbr), n_rows, _ptr(bias),
-                                     out.data_ptr(), _ptr(ws), nbytes, _stream()), "conv_gather_gemm")
+                                     c_out, int(transpose_w), int(flip_k), _ptr(nbr), _ptr(tile_mask), n_rows,
+                                     _ptr(bias), out.data_ptr(), _ptr(ws), nbytes, _stream()),
+              "conv_gather_gemm")
     return out
 
 

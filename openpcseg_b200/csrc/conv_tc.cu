@@ -16,121 +16,13 @@
 // Roofline: tensor pipe for C >= 128 layers; L2->SM gather bandwidth / LDGSTS
 // issue for narrow layers.  Algorithmic FLOPs = 2 * M * C_in * C_out (M = map pairs);
 // algorithmic bytes = 2*C_red*M (gathered rows) + 2*C_res*N_rows + 4*K*N_rows + 2*K*C_in*C_out.
-#include "common.cuh"
+#include <stdlib.h>
+
+#include "tc_common.cuh"
 
 namespace b2s {
 
 namespace tc {
-
-constexpr int kTileM = 128;
-constexpr int kProducerThreads = 128;
-constexpr int kThreads = 160;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
-               "r"(cols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols)
-               : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                         uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-        "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// Shared-memory matrix descriptor, K-major operand, rows of ROWB bytes (128 -> SWIZZLE_128B,
-// 64 -> SWIZZLE_64B), 8-row groups contiguous (SBO = 8 * ROWB).  Field layout: cute
-// UMMA::SmemDescriptor (start>>4 @0, LBO>>4 @16, SBO>>4 @32, version=1 @46, layout @61).
-template <int ROWB>
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  constexpr uint64_t layout = ROWB == 128 ? 2 : (ROWB == 64 ? 4 : 6);
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-  d |= (uint64_t)1 << 16;                       // LBO (ignored for swizzled K-major)
-  d |= (uint64_t)((8 * ROWB) >> 4) << 32;       // SBO
-  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
-  d |= layout << 61;
-  return d;
-}
-
-// kind::f16 instruction descriptor: D=F32, A=B=F16, both K-major, M=128.
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-}
-
-// byte offset of (row, 16-byte chunk) inside a swizzled K-major tile with ROWB-byte rows
-template <int ROWB>
-__device__ __forceinline__ uint32_t swz(int row, int chunk) {
-  if constexpr (ROWB == 128) return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
-  else return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
-}
 
 struct Params {
   const __half* in;     // [n_src, c_red]
@@ -339,6 +231,19 @@ static int tmem_cols_for(int n) {
 
 }  // namespace tc
 
+int launch_gather_gemm_tc2(const void* in, const void* wt, int k, int c_red, int c_res, int flip_k,
+                           const int32_t* nbr, const uint32_t* tile_mask, int64_t n_rows,
+                           const void* bias, void* out, cudaStream_t st);
+
+static bool use_v1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2S_TC_V1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 bool tc_gather_gemm_supported(int c_red, int c_res) {
   if (c_red % 32 != 0 || c_red < 32) return false;
   if (c_res % 16 != 0 || c_res < 16 || c_res > 512) return false;
@@ -351,8 +256,9 @@ size_t tc_gather_gemm_workspace(int k, int c_in, int c_out) {
 }
 
 int launch_gather_gemm_tc(const void* in, const void* weight, int k, int c_in, int c_out,
-                          int transpose_w, int flip_k, const int32_t* nbr, int64_t n_rows,
-                          const void* bias, void* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+                          int transpose_w, int flip_k, const int32_t* nbr, const uint32_t* tile_mask,
+                          int64_t n_rows, const void* bias, void* out, void* ws, size_t ws_bytes,
+                          cudaStream_t st) {
   using namespace tc;
   const int c_red = transpose_w ? c_out : c_in, c_res = transpose_w ? c_in : c_out;
   const __half* wt = reinterpret_cast<const __half*>(weight);
@@ -365,6 +271,9 @@ int launch_gather_gemm_tc(const void* in, const void* weight, int k, int c_in, i
     transpose_weight_kernel<<<g, 256, 0, st>>>(wt, reinterpret_cast<__half*>(ws), c_in, c_out);
     wt = reinterpret_cast<const __half*>(ws);
   }  // input gradient: B_k[n = c_in][c = c_out] = W[k][n][c] is the stored layout already
+  if (!use_v1())
+    return launch_gather_gemm_tc2(in, wt, k, c_red, c_res, flip_k, nbr, tile_mask, n_rows, bias, out,
+                                  st);
   Params p;
   p.in = reinterpret_cast<const __half*>(in);
   p.wt = wt;
@@ -489,7 +398,8 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p) {
   const int total_units = s_units[p.kvol] * p.m_tiles;
   const int n_half = p.c_out > 256 ? p.c_out / 2 : p.c_out;
 
-  int it = 0;            // global stage counter (ring position / phases continue across units)
+  // ring position shared by the roles (each role advances its own copy identically)
+  int rs = 0, rwraps = 0;
   int unit_no = 0;       // units processed by this CTA (phase of s_acc)
   for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++unit_no) {
     const int mt = unit % p.m_tiles;
@@ -504,13 +414,12 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p) {
 
     if (warp < 4) {
       // ---------------------------------------------------------------- producers
-      const int LAG = S >= 3 ? 2 : 1;
       const int sub = lane >> 3, chunk = lane & 7;
       const int2* pr = reinterpret_cast<const int2*>(p.pairs);
-      for (int st = 0; st < n_stage; ++st, ++it) {
-        const int s = it % S;
-        if (it >= S) mbar_wait(smem_u32(&s_empty[s]), ((it / S) - 1) & 1);
-        const uint32_t a_base = smem_base + s * stage_stride;
+      const int64_t base_q = s_start[k] + lo + warp * 16 + lane;
+      for (int st = 0; st < n_stage; ++st) {
+        if (rwraps > 0) mbar_wait(smem_u32(&s_empty[rs]), (rwraps - 1) & 1);
+        const uint32_t a_base = smem_base + rs * stage_stride;
         const uint32_t b_base = a_base + a_bytes;
         // this warp stages rows [warp*16, warp*16+16) of the 64-pair stage
         int32_t my_i = -1, my_o = -1;
@@ -518,7 +427,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p) {
           const int64_t q = lo + (int64_t)st * kRows + warp * 16 + lane;
           if (q < hi) {
             if (pr) {
-              int2 v = __ldg(pr + s_start[k] + q);
+              int2 v = __ldg(pr + base_q + (int64_t)st * kRows);
               my_i = p.swap_pairs ? v.y : v.x;
               my_o = p.swap_pairs ? v.x : v.y;
             } else {
@@ -549,18 +458,11 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p) {
                          o >= 0 ? p.gy + (int64_t)o * p.c_out + ch : p.gy, o >= 0 ? 16u : 0u);
           }
         }
-        cp_async_commit();
-        if (st >= LAG) {
-          if (LAG == 2) cp_async_wait<2>();
-          else cp_async_wait<1>();
-          fence_proxy_async();
-          mbar_arrive(smem_u32(&s_full[(it - LAG) % S]));
-        }
+        // the copy engine signals the stage when this thread's gathers have landed
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&s_full[rs]))
+                     : "memory");
+        if (++rs == S) { rs = 0; ++rwraps; }
       }
-      cp_async_wait<0>();
-      fence_proxy_async();
-      for (int j = (n_stage > LAG ? n_stage - LAG : 0); j < n_stage; ++j)
-        mbar_arrive(smem_u32(&s_full[(it - n_stage + j) % S]));
 
       // ----------------------------------------------------------------- epilogue
       mbar_wait(smem_u32(&s_acc), unit_no & 1);
@@ -583,12 +485,12 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p) {
     } else {
       // --------------------------------------------------------------- MMA issuer
       const uint32_t idesc = make_idesc_mn(n_half);
-      for (int st = 0; st < n_stage; ++st, ++it) {
-        const int s = it % S;
-        mbar_wait(smem_u32(&s_full[s]), (it / S) & 1);
+      for (int st = 0; st < n_stage; ++st) {
+        mbar_wait(smem_u32(&s_full[rs]), rwraps & 1);
+        fence_proxy_async();           // rows were written through the generic proxy (cp.async)
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t a_base = smem_base + s * stage_stride;
+          const uint32_t a_base = smem_base + rs * stage_stride;
           const uint32_t b_base = a_base + a_bytes;
 #pragma unroll
           for (int kk = 0; kk < kRows / 16; ++kk) {
@@ -601,10 +503,11 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p) {
               umma_f16(tmem_acc + (uint32_t)n_half, ad, bd2, idesc, (st | kk) ? 1u : 0u);
             }
           }
-          umma_commit(smem_u32(&s_empty[s]));
+          umma_commit(smem_u32(&s_empty[rs]));
           if (st == n_stage - 1) umma_commit(smem_u32(&s_acc));
         }
         __syncwarp();
+        if (++rs == S) { rs = 0; ++rwraps; }
       }
     }
   }
@@ -644,7 +547,9 @@ int launch_wgrad_tc(const void* in, const void* gout, const int32_t* nbmaps,
   p.m_tiles = (c_in + 127) / 128;
   p.tmem_cols = tc::tmem_cols_for(c_out);
   const int stage = (2 + (c_out + 63) / 64) * kPanelBytes;
-  int stages = (int)((220 * 1024) / stage);
+  int stages = (int)((110 * 1024) / stage);          // two CTAs per SM when >= 3 stages fit twice
+  const bool two_per_sm = stages >= 3 && p.tmem_cols <= 256;
+  if (!two_per_sm) stages = (int)((220 * 1024) / stage);
   if (stages > 6) stages = 6;
   B2S_REQUIRE(stages >= 2, B2S_ERR_UNSUPPORTED, "b2s_conv_wgrad: tile does not fit (C_out=%d)", c_out);
   p.stages = stages;
@@ -660,7 +565,8 @@ int launch_wgrad_tc(const void* in, const void* gout, const int32_t* nbmaps,
   const size_t smem = (size_t)stages * stage + 1024;
   cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int64_t max_units = (n_pairs_bound / unit + k) * p.m_tiles;
-  int grid = (int)(max_units < sms ? (max_units < 1 ? 1 : max_units) : sms);
+  const int64_t slots = (int64_t)sms * (two_per_sm ? 2 : 1);
+  int grid = (int)(max_units < slots ? (max_units < 1 ? 1 : max_units) : slots);
   wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(p);
   return B2S_OK;
 }

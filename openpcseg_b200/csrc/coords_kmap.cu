@@ -151,7 +151,9 @@ __global__ void __launch_bounds__(256) unpack_kernel(const uint64_t* __restrict_
 __global__ void __launch_bounds__(256) kmap_probe_kernel(
     TableView table, const int4* __restrict__ out_coords, int64_t n_out, int64_t n_in,
     const int32_t* __restrict__ offsets, int kvol, int32_t* __restrict__ nbr_out,
-    int32_t* __restrict__ nbr_in, int32_t* __restrict__ nbsizes) {
+    int32_t* __restrict__ nbr_in, int32_t* __restrict__ nbsizes, uint32_t* __restrict__ mask_out,
+    uint32_t* __restrict__ mask_in) {
+  const int words = (kvol + 31) >> 5;
   extern __shared__ int32_t s_mem[];
   int32_t* s_off = s_mem;             // 3*kvol
   int32_t* s_cnt = s_mem + 3 * kvol;  // kvol
@@ -171,10 +173,17 @@ __global__ void __launch_bounds__(256) kmap_probe_kernel(
         hit = table_find(table, coord_hash(c.x + s_off[3 * k], c.y + s_off[3 * k + 1],
                                            c.z + s_off[3 * k + 2], c.w));
         nbr_out[(int64_t)k * n_out + o] = hit;
-        if (hit >= 0 && nbr_in) nbr_in[(int64_t)k * n_in + hit] = (int32_t)o;
+        if (hit >= 0 && nbr_in) {
+          nbr_in[(int64_t)k * n_in + hit] = (int32_t)o;
+          if (mask_in) atomicOr(mask_in + (int64_t)(hit >> 7) * words + (k >> 5), 1u << (k & 31));
+        }
       }
       unsigned m = __ballot_sync(0xffffffffu, hit >= 0);
-      if (lane == 0 && m) atomicAdd(s_cnt + k, __popc(m));
+      if (lane == 0 && m) {
+        atomicAdd(s_cnt + k, __popc(m));
+        // a warp's 32 rows lie inside one 128-row tile (o is warp-aligned)
+        if (mask_out) atomicOr(mask_out + (o >> 7) * words + (k >> 5), 1u << (k & 31));
+      }
     }
   }
   __syncthreads();
@@ -348,8 +357,8 @@ size_t b2s_kmap_workspace_bytes(int64_t n_in, int64_t n_out, int32_t k) {
 
 int b2s_kmap_build(const int32_t* in_coords, int64_t n_in, const int32_t* out_coords,
                    int64_t n_out, const int32_t* offsets, int32_t k, int32_t* nbr_out,
-                   int32_t* nbr_in, int32_t* nbsizes, void* ws, size_t ws_bytes,
-                   b2s_stream_t stream) {
+                   int32_t* nbr_in, int32_t* nbsizes, uint32_t* tile_mask_out,
+                   uint32_t* tile_mask_in, void* ws, size_t ws_bytes, b2s_stream_t stream) {
   B2S_REQUIRE(n_in >= 0 && n_out >= 0 && k >= 1 && k <= 2048, B2S_ERR_INVALID,
               "b2s_kmap_build: bad sizes (n_in=%lld n_out=%lld k=%d)", (long long)n_in,
               (long long)n_out, k);
@@ -361,6 +370,11 @@ int b2s_kmap_build(const int32_t* in_coords, int64_t n_in, const int32_t* out_co
   cudaStream_t st = as_stream(stream);
   cudaMemsetAsync(nbsizes, 0, k * sizeof(int32_t), st);
   if (nbr_in && n_in > 0) cudaMemsetAsync(nbr_in, 0xFF, (size_t)k * n_in * sizeof(int32_t), st);
+  const size_t words = (size_t)(k + 31) / 32;
+  if (tile_mask_out && n_out > 0)
+    cudaMemsetAsync(tile_mask_out, 0, (size_t)ceil_div(n_out, 128) * words * 4, st);
+  if (tile_mask_in && n_in > 0)
+    cudaMemsetAsync(tile_mask_in, 0, (size_t)ceil_div(n_in, 128) * words * 4, st);
   if (n_out == 0) return B2S_OK;
   B2S_REQUIRE(out_coords && nbr_out && (n_in == 0 || in_coords), B2S_ERR_INVALID,
               "b2s_kmap_build: null pointer");
@@ -369,7 +383,7 @@ int b2s_kmap_build(const int32_t* in_coords, int64_t n_in, const int32_t* out_co
   TableView t = table_view(ws, n_in);
   kmap_probe_kernel<<<grid_for(n_out, 256), 256, 4 * k * sizeof(int32_t), st>>>(
       t, reinterpret_cast<const int4*>(out_coords), n_out, n_in, offsets, k, nbr_out, nbr_in,
-      nbsizes);
+      nbsizes, tile_mask_out, nbr_in ? tile_mask_in : nullptr);
   B2S_CHECK_LAUNCH("b2s_kmap_build");
   return B2S_OK;
 }

@@ -117,9 +117,12 @@ class KernelMap:
     gather maps and the padded int32 pair buffer directly.
     """
 
-    def __init__(self, nbr_out, nbr_in, nbsizes, sizes: Tuple[int, int], symmetric: bool):
+    def __init__(self, nbr_out, nbr_in, nbsizes, sizes: Tuple[int, int], symmetric: bool,
+                 mask_out=None, mask_in=None):
         self.nbr_out = nbr_out          # int32 [K, N_out]: input row per (offset, output row)
         self.nbr_in = nbr_in            # int32 [K, N_in ]: output row per (offset, input row) | None
+        self.mask_out = mask_out        # active-offset bits per 128-row tile of nbr_out
+        self.mask_in = mask_in          # ... of nbr_in
         self.nbsizes32 = nbsizes        # int32 [K] on device
         self.sizes = sizes
         self.symmetric = symmetric      # nbr_in[k] == nbr_out[K-1-k] (submanifold, odd kernel)
@@ -136,11 +139,11 @@ class KernelMap:
         """Device scalar with the pair count M (used by the measurement hooks only)."""
         return self.pairs()[1] if B.PROFILER is not None else None
 
-    def in_gather_map(self) -> Tuple[torch.Tensor, bool]:
-        """(map [K, N_in], flip_k) giving, per input row, the output row it feeds."""
+    def in_gather_map(self):
+        """(map [K, N_in], flip_k, tile mask) giving, per input row, the output row it feeds."""
         if self.symmetric:
-            return self.nbr_out, True
-        return self.nbr_in, False
+            return self.nbr_out, True, self.mask_out
+        return self.nbr_in, False, self.mask_in
 
     def reference_format(self):
         if self._ref is None:
@@ -167,8 +170,10 @@ def build_kernel_map(in_coords: torch.Tensor, out_coords: torch.Tensor, kernel_s
     same = (in_coords is out_coords) or (in_coords.data_ptr() == out_coords.data_ptr()
                                           and in_coords.shape == out_coords.shape)
     symmetric = bool(same and all(k % 2 == 1 for k in kernel_size))
-    nbr_out, nbr_in, nbsizes = B.kmap_build(in_coords, out_coords, offsets, want_nbr_in=not symmetric)
-    return KernelMap(nbr_out, nbr_in, nbsizes, (in_coords.shape[0], out_coords.shape[0]), symmetric)
+    nbr_out, nbr_in, nbsizes, mask_out, mask_in = B.kmap_build(in_coords, out_coords, offsets,
+                                                               want_nbr_in=not symmetric)
+    return KernelMap(nbr_out, nbr_in, nbsizes, (in_coords.shape[0], out_coords.shape[0]), symmetric,
+                     mask_out, mask_in)
 
 
 # ---------------------------------------------------------------------- convolution
@@ -185,10 +190,12 @@ class ConvolutionFunction(Function):
         w = weight.to(feats.dtype)
         hint = kmap.total_hint()
         if not transposed:
-            out = B.conv_gather_gemm(feats, w, kmap.nbr_out, kmap.sizes[1], False, False, pairs_hint=hint)
+            out = B.conv_gather_gemm(feats, w, kmap.nbr_out, kmap.sizes[1], False, False, pairs_hint=hint,
+                                     tile_mask=kmap.mask_out)
         else:
-            gmap, flip = kmap.in_gather_map()
-            out = B.conv_gather_gemm(feats, w, gmap, kmap.sizes[0], False, flip, pairs_hint=hint)
+            gmap, flip, mask = kmap.in_gather_map()
+            out = B.conv_gather_gemm(feats, w, gmap, kmap.sizes[0], False, flip, pairs_hint=hint,
+                                     tile_mask=mask)
         ctx.save_for_backward(feats, weight)
         ctx.kmap, ctx.transposed = kmap, transposed
         return out
@@ -204,11 +211,12 @@ class ConvolutionFunction(Function):
         hint = kmap.total_hint()
         if ctx.needs_input_grad[0]:
             if not transposed:
-                gmap, flip = kmap.in_gather_map()
-                grad_in = B.conv_gather_gemm(grad_out, w, gmap, kmap.sizes[0], True, flip, pairs_hint=hint)
+                gmap, flip, mask = kmap.in_gather_map()
+                grad_in = B.conv_gather_gemm(grad_out, w, gmap, kmap.sizes[0], True, flip, pairs_hint=hint,
+                                             tile_mask=mask)
             else:
                 grad_in = B.conv_gather_gemm(grad_out, w, kmap.nbr_out, kmap.sizes[1], True, False,
-                                             pairs_hint=hint)
+                                             pairs_hint=hint, tile_mask=kmap.mask_out)
         if ctx.needs_input_grad[1]:
             pairs, _ = kmap.pairs()
             grad_w = B.conv_wgrad(feats, grad_out, kmap.kvol, pairs, kmap.nbsizes32, transposed,

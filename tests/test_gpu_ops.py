@@ -132,9 +132,16 @@ def test_kmap_golden_submanifold(ts, golden, tag, ks):
     assert eq(nbmaps, g[f"{tag}_nbmaps"]) and eq(nbsizes, g[f"{tag}_nbsizes"])
     assert sizes == (c.shape[0], c.shape[0])
     # symmetric maps: nbr_in[k] == nbr_out[K-1-k]
-    _, nbr_in, _ = __import__("openpcseg_b200").backend.kmap_build(
+    _, nbr_in, _, mask_out, mask_in = __import__("openpcseg_b200").backend.kmap_build(
         c, c, ts.nn.utils.get_kernel_offsets(ks, 1, 1, "cuda"), True)
     assert torch.equal(nbr_in, km.nbr_out.flip(0))
+    # tile masks: bit k of tile t <=> some row of the tile has a neighbour for offset k
+    for nbr, mask in ((km.nbr_out, mask_out), (nbr_in, mask_in)):
+        kv, n = nbr.shape
+        pad = (-n) % 128
+        have = torch.nn.functional.pad(nbr >= 0, (0, pad)).view(kv, -1, 128).any(2)      # [K, tiles]
+        bits = (have.t().long() << torch.arange(kv, device="cuda")).sum(1)
+        assert torch.equal(bits, mask[:, 0].long() & 0xFFFFFFFF)
 
 
 def test_kmap_multibatch_and_strided(ts, golden):
