@@ -175,6 +175,24 @@ int b2s_trilinear_map(const float* pts, int64_t n_pts, int32_t stride, const voi
 int b2s_ti_weights(const float* pts, int64_t n_pts, const int64_t* idx, float scale, float* w,
                    b2s_stream_t stream);
 
+/* ------------------------------------------------- fused batch norm ("next" N1) ---
+ * Training-mode BatchNorm1d over the rows of [n, c] voxel features, fused with an optional
+ * residual add and ReLU:  y = act(bn(x) [+ residual])  - what the voxel segmentors apply
+ * after every sparse conv (nn.BatchNorm1d through fapply, minkunet.py:27-29; add + ReLU of
+ * the residual block, minkunet.py:134-136).  gamma/beta/running_* are fp32 [c] (running_*
+ * may be NULL); mean/invstd fp32 [c] are saved for backward; scale_shift fp32 [2][c] and
+ * sums fp64 [2][c] are scratch.  Backward: dy, y (needed when relu), x -> dx (and dres = the
+ * gradient of the residual input, may be NULL); on return sums[0][c] = d_beta, sums[1][c] =
+ * d_gamma.  c must be a multiple of the 16-byte vector (8 for fp16, 4 for fp32).            */
+int b2s_bn_supported(int32_t dtype, int32_t c);
+int b2s_bn_forward(int32_t dtype, const void* x, const void* residual, int64_t n, int32_t c,
+                   const float* gamma, const float* beta, float eps, float momentum,
+                   float* running_mean, float* running_var, int32_t relu, void* y, float* mean,
+                   float* invstd, float* scale_shift, double* sums, b2s_stream_t stream);
+int b2s_bn_backward(int32_t dtype, const void* dy, const void* y, const void* x, int64_t n, int32_t c,
+                    const float* mean, const float* invstd, const float* gamma, int32_t relu, void* dx,
+                    void* dres, double* sums, b2s_stream_t stream);
+
 /* --------------------------------------------------------- range-image ops ---
  * RPVNet: replaces map_count_forward / denselize_forward / denselize_backward
  * (range_lib/range_utils/src/map_count_gpu.cu:5-14, denselize_gpu.cu:5-34).

@@ -386,6 +386,48 @@ def ti_weights(pts: torch.Tensor, idx_query: torch.Tensor, scale: float) -> torc
     return w
 
 
+# ---------------------------------------------------------------- fused batch norm
+def bn_supported(x: torch.Tensor) -> bool:
+    return (x.is_cuda and x.dtype in (torch.float16, torch.float32) and x.ndim == 2 and x.shape[0] > 0
+            and bool(_lib.lib().b2s_bn_supported(_dtype_code(x), x.shape[1])))
+
+
+def bn_forward(x: torch.Tensor, residual: Optional[torch.Tensor], gamma, beta, running_mean, running_var,
+               eps: float, momentum: float, relu: bool):
+    """y = act(bn_train(x) [+ residual]); returns (y, mean, invstd)."""
+    _cuda(x, residual, gamma, beta, running_mean, running_var)
+    x = x.contiguous()
+    if residual is not None:
+        residual = residual.contiguous()
+        assert residual.shape == x.shape and residual.dtype == x.dtype
+    n, c = x.shape
+    y = torch.empty_like(x)
+    stat = torch.empty((4, c), dtype=torch.float32, device=x.device)     # mean, invstd, scale, shift
+    sums = torch.empty((2, c), dtype=torch.float64, device=x.device)
+    check(_lib.lib().b2s_bn_forward(_dtype_code(x), x.data_ptr(), _ptr(residual), n, c, _ptr(gamma),
+                                    _ptr(beta), float(eps), float(momentum), _ptr(running_mean),
+                                    _ptr(running_var), int(relu), y.data_ptr(), stat[0].data_ptr(),
+                                    stat[1].data_ptr(), stat[2].data_ptr(), sums.data_ptr(), _stream()),
+          "bn_forward", launches=3)
+    return y, stat[0], stat[1]
+
+
+def bn_backward(dy: torch.Tensor, y: Optional[torch.Tensor], x: torch.Tensor, mean, invstd, gamma,
+                relu: bool, want_dres: bool):
+    """Returns (dx, dres | None, d_gamma fp32 [c], d_beta fp32 [c])."""
+    _cuda(dy, y, x)
+    dy = dy.contiguous()
+    n, c = x.shape
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_dres else None
+    sums = torch.empty((2, c), dtype=torch.float64, device=x.device)
+    check(_lib.lib().b2s_bn_backward(_dtype_code(x), dy.data_ptr(), _ptr(y), x.data_ptr(), n, c,
+                                     mean.data_ptr(), invstd.data_ptr(), _ptr(gamma), int(relu),
+                                     dx.data_ptr(), _ptr(dres), sums.data_ptr(), _stream()),
+          "bn_backward", launches=2)
+    return dx, dres, sums[1].float(), sums[0].float()
+
+
 # ------------------------------------------------------------------- range-image ops
 def map_count(pxpy: torch.Tensor, b: int, h: int, w: int) -> torch.Tensor:
     _cuda(pxpy)

@@ -18,6 +18,7 @@ from torch import nn
 
 from .. import torchsparse as ts
 from ..torchsparse import nn as spnn
+from ..torchsparse.nn.functional import batch_norm_act
 from ..torchsparse import PointTensor
 from .losses import SegLoss
 from .point_voxel import initial_voxelize, voxel_to_point
@@ -59,6 +60,12 @@ class _SparseSyncBN(nn.SyncBatchNorm):
         return x._like(super().forward(x.feats))
 
 
+def _conv_bn(conv, bn, x, relu=True, residual=None):
+    """conv -> fused (batch norm [+ residual] [+ ReLU]) on the conv's output rows."""
+    y = conv(x)
+    return y._like(batch_norm_act(y.feats, bn, relu=relu, residual=residual))
+
+
 def _bn(c: int, sync: bool) -> nn.Module:
     return _SparseSyncBN(c) if sync else _SparseBN(c)
 
@@ -71,8 +78,8 @@ class ConvBlock(nn.Module):
         self.net = nn.Sequential(spnn.Conv3d(inc, outc, kernel_size=ks, stride=stride,
                                              transposed=transposed), _bn(outc, sync), spnn.ReLU(True))
 
-    def forward(self, x):
-        return self.net(x)
+    def forward(self, x):                     # net = (conv, bn, relu): BN + ReLU run fused
+        return _conv_bn(self.net[0], self.net[1], x)
 
 
 class ResidualBlock(nn.Module):
@@ -88,8 +95,13 @@ class ResidualBlock(nn.Module):
             self.downsample = nn.Sequential(spnn.Conv3d(inc, outc, kernel_size=1), _bn(outc, sync))
         self.relu = spnn.ReLU(True)
 
-    def forward(self, x):
-        return self.relu(self.net(x) + self.downsample(x))
+    def forward(self, x):                     # relu(bn(conv(relu(bn(conv x)))) + shortcut(x))
+        y = _conv_bn(self.net[0], self.net[1], x)
+        if isinstance(self.downsample, nn.Identity):
+            shortcut = x.feats
+        else:
+            shortcut = _conv_bn(self.downsample[0], self.downsample[1], x, relu=False).feats
+        return _conv_bn(self.net[3], self.net[4], y, relu=True, residual=shortcut)
 
 
 def _res_layers(inc: int, outc: int, n: int, sync: bool) -> List[nn.Module]:
@@ -127,7 +139,9 @@ class MinkUNet(nn.Module):
     def forward_logits(self, lidar: ts.SparseTensor) -> torch.Tensor:
         feats = lidar.F[:, : self.cfg.in_feature_dim]
         z = PointTensor(feats, lidar.C.float())
-        x0 = self.stem(initial_voxelize(z, self.cfg.pres, self.cfg.vres))
+        x0 = initial_voxelize(z, self.cfg.pres, self.cfg.vres)
+        x0 = _conv_bn(self.stem[0], self.stem[1], x0)
+        x0 = _conv_bn(self.stem[3], self.stem[4], x0)
         z0 = voxel_to_point(x0, z)
         x1 = self.stage1(x0)
         x2 = self.stage2(x1)

@@ -248,6 +248,21 @@ class _DenseConv(Function):
         return grad_in, grad_w
 
 
+def _pad_for_tensor_cores(feats: torch.Tensor, weight: torch.Tensor):
+    """fp16 only: zero-pad C_in to a multiple of 32 and C_out to a multiple of 16 so narrow layers
+    (the 4-channel stem, 20-class heads) run on the tcgen05 kernels instead of the CUDA-core
+    family; zero channels change nothing and autograd slices the gradients back."""
+    if feats.dtype != torch.float16:
+        return feats, weight, None
+    c_in, c_out = weight.shape[-2], weight.shape[-1]
+    pad_in, pad_out = (-c_in) % 32, (-c_out) % 16
+    if pad_in == 0 and pad_out == 0:
+        return feats, weight, None
+    feats = torch.nn.functional.pad(feats, (0, pad_in))
+    weight = torch.nn.functional.pad(weight, (0, pad_out, 0, pad_in))
+    return feats, weight, (c_out if pad_out else None)
+
+
 def conv3d(input: SparseTensor, weight: torch.Tensor,
            kernel_size: Union[int, List[int], Tuple[int, ...]], bias: Optional[torch.Tensor] = None,
            stride: Union[int, List[int], Tuple[int, ...]] = 1,
@@ -257,7 +272,7 @@ def conv3d(input: SparseTensor, weight: torch.Tensor,
     kernel_size = make_ntuple(kernel_size, ndim=3)
     stride = make_ntuple(stride, ndim=3)
     dilation = make_ntuple(dilation, ndim=3)
-    feats = _amp_half(input.feats)
+    feats, weight, keep_out = _pad_for_tensor_cores(_amp_half(input.feats), weight)
     ones = (1, 1, 1)
 
     if kernel_size == ones and stride == ones and dilation == ones:
@@ -282,6 +297,8 @@ def conv3d(input: SparseTensor, weight: torch.Tensor,
         kmap = input.kmaps[(out_stride, kernel_size, stride, dilation)]
         out_feats = ConvolutionFunction.apply(feats, weight, kmap, True)
 
+    if keep_out is not None:
+        out_feats = out_feats[:, :keep_out]
     if bias is not None:
         out_feats = out_feats + bias.to(out_feats.dtype)
 
@@ -300,3 +317,45 @@ def relu(input: SparseTensor, inplace: bool = True) -> SparseTensor:
 def leaky_relu(input: SparseTensor, negative_slope: float = 0.1, inplace: bool = True) -> SparseTensor:
     return fapply(input, torch.nn.functional.leaky_relu, negative_slope=negative_slope,
                   inplace=inplace)
+
+
+# ------------------------------------------------------ fused batch norm (+add, +ReLU)
+class _BatchNormAct(Function):
+    """y = act(batch_norm_train(x) [+ residual]) in two kernels forward / two backward."""
+
+    @staticmethod
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, eps, momentum, relu):
+        y, mean, invstd = B.bn_forward(x, residual, gamma, beta, running_mean, running_var, eps, momentum,
+                                       relu)
+        ctx.save_for_backward(x, y if relu else None, mean, invstd, gamma)
+        ctx.relu, ctx.has_res = relu, residual is not None
+        ctx.mark_non_differentiable(mean, invstd)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, y, mean, invstd, gamma = ctx.saved_tensors
+        dx, dres, dgamma, dbeta = B.bn_backward(dy, y, x, mean, invstd, gamma, ctx.relu,
+                                                ctx.has_res and ctx.needs_input_grad[1])
+        return (dx, dres, dgamma.to(gamma.dtype) if gamma is not None else None,
+                dbeta.to(gamma.dtype) if gamma is not None else None, None, None, None, None, None)
+
+
+def batch_norm_act(x: torch.Tensor, bn: torch.nn.modules.batchnorm._BatchNorm, relu: bool = False,
+                   residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused training-mode batch norm of [N, C] rows with optional residual add and ReLU, same
+    numerics contract as ``relu(bn(x) + residual)``.  Falls back to the stock modules in eval mode,
+    for SyncBatchNorm under a process group, or for channel counts the kernels do not tile."""
+    sync = isinstance(bn, torch.nn.SyncBatchNorm) and torch.distributed.is_available() and \
+        torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+    if (not bn.training) or sync or not bn.track_running_stats or bn.momentum is None \
+            or not B.bn_supported(x) or (residual is not None and residual.dtype != x.dtype):
+        y = bn(x)
+        if residual is not None:
+            y = y + residual
+        return torch.relu(y) if relu else y
+    with torch.no_grad():
+        bn.num_batches_tracked += 1
+    return _BatchNormAct.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
+                               bn.momentum, relu)

@@ -432,3 +432,45 @@ def test_tc_matches_simt_bitwise_maps_and_close_values(ts):
     with torch.autocast("cuda", dtype=torch.float16):
         y16 = F.conv3d(_sparse(ts, dev(x, torch.float16), dev(c)), dev(w), 3).feats
     assert rel_err(y16, y32) < FP16_TOL
+
+
+# ----------------------------------------------------------------- fused batch norm
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("c,relu,with_res", [(32, True, False), (96, True, True), (256, False, False),
+                                              (64, False, True)])
+def test_fused_batch_norm_act(ts, dtype, c, relu, with_res):
+    F = ts.nn.functional
+    torch.manual_seed(c)
+    n = 5000
+    tol = 2e-5 if dtype == torch.float32 else 2e-3
+    x = (torch.randn(n, c, device="cuda") * 2 + 0.5).to(dtype)
+    res = torch.randn(n, c, device="cuda").to(dtype) if with_res else None
+    dy = torch.randn(n, c, device="cuda").to(dtype)
+    bn_a, bn_b = torch.nn.BatchNorm1d(c).cuda(), torch.nn.BatchNorm1d(c).cuda()
+    with torch.no_grad():
+        bn_a.weight.uniform_(0.5, 1.5)
+        bn_a.bias.uniform_(-0.5, 0.5)
+    bn_b.load_state_dict(bn_a.state_dict())
+    xa, xb = x.clone().requires_grad_(True), x.float().clone().requires_grad_(True)
+    ra = res.clone().requires_grad_(True) if with_res else None
+    rb = res.float().clone().requires_grad_(True) if with_res else None
+    ya = F.batch_norm_act(xa, bn_a, relu=relu, residual=ra)
+    yb = bn_b(xb)                                   # fp32 torch reference on the same (rounded) inputs
+    if with_res:
+        yb = yb + rb
+    if relu:
+        yb = torch.relu(yb)
+    assert ya.dtype == dtype and rel_err(ya, yb) < tol
+    ya.backward(dy)
+    yb.backward(dy.float())
+    assert rel_err(xa.grad, xb.grad) < 5 * tol
+    if with_res:
+        assert rel_err(ra.grad, rb.grad) < tol
+    assert rel_err(bn_a.weight.grad, bn_b.weight.grad) < 5 * tol
+    assert rel_err(bn_a.bias.grad, bn_b.bias.grad) < 5 * tol
+    assert rel_err(bn_a.running_mean, bn_b.running_mean) < tol
+    assert rel_err(bn_a.running_var, bn_b.running_var) < tol
+    assert int(bn_a.num_batches_tracked) == 1
+    # eval mode falls back to the stock module
+    bn_a.eval()
+    assert F.batch_norm_act(x, bn_a, relu=relu).shape == x.shape
