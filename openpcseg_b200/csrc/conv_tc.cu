@@ -235,6 +235,19 @@ int launch_gather_gemm_tc2(const void* in, const void* wt, int k, int c_red, int
                            const int32_t* nbr, const uint32_t* tile_mask, int64_t n_rows,
                            const void* bias, void* out, cudaStream_t st);
 
+int launch_gather_gemm_tc3(const void* in, const void* wt, int k, int c_red, int c_res, int flip_k,
+                           const int32_t* nbr, const uint32_t* tile_mask, int64_t n_rows,
+                           const void* bias, void* out, cudaStream_t st);
+
+static bool use_v2() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2S_TC_V2");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 static bool use_v1() {
   static int v = -1;
   if (v < 0) {
@@ -271,6 +284,9 @@ int launch_gather_gemm_tc(const void* in, const void* weight, int k, int c_in, i
     transpose_weight_kernel<<<g, 256, 0, st>>>(wt, reinterpret_cast<__half*>(ws), c_in, c_out);
     wt = reinterpret_cast<const __half*>(ws);
   }  // input gradient: B_k[n = c_in][c = c_out] = W[k][n][c] is the stored layout already
+  if (!use_v1() && !use_v2() && nbr && tile_mask)      // persistent kernel (needs the tile masks)
+    return launch_gather_gemm_tc3(in, wt, k, c_red, c_res, flip_k, nbr, tile_mask, n_rows, bias, out,
+                                  st);
   if (!use_v1())
     return launch_gather_gemm_tc2(in, wt, k, c_red, c_res, flip_k, nbr, tile_mask, n_rows, bias, out,
                                   st);

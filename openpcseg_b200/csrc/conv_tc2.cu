@@ -55,6 +55,8 @@ struct Params {
   int64_t n_rows;
   int kvol, c_red, c_res, flip_k;
   int n64, tail32;      // c_red = 64 * n64 + 32 * tail32
+  int dbg;              // bit0: zero-fill all A rows, bit1: no A copies, bit2: no B TMA, bit3: no MMA
+  int consumer_fence;   // debugging aid: generic->async proxy fence in the MMA warp per stage
   int sa, sb;           // ring depths: A (gathered rows, deep: hides the gather latency), B (weights)
   int b_stride;         // bytes of one B slot (multiple of 1024)
   int tmem_cols;
@@ -82,7 +84,9 @@ __device__ __forceinline__ void gather_chunk(const Params& p, int32_t my_src, ui
 #pragma unroll
   for (int i = 0; i < CH; ++i) {
     const int rl = i * RPI + sub;
-    const int32_t src = __shfl_sync(0xffffffffu, my_src, rl);
+    int32_t src = __shfl_sync(0xffffffffu, my_src, rl);
+    if (p.dbg & 1) src = -1;
+    if (p.dbg & 2) continue;
     const __half* g = src >= 0 ? base + (int64_t)src * p.c_red : p.in;
     cp_async16(a_base + swz<ROWB>(warp * 32 + rl, chunk), g, src >= 0 ? 16u : 0u);
   }
@@ -118,8 +122,8 @@ __global__ void __launch_bounds__(kThreads2) gather_gemm_tc2_kernel(
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ __align__(8) uint64_t s_full[8];     // A slots: 128 gather-thread arrivals
   __shared__ __align__(8) uint64_t s_empty[8];
-  __shared__ __align__(8) uint64_t s_fullb[4];    // B slots: TMA expect_tx
-  __shared__ __align__(8) uint64_t s_emptyb[4];
+  __shared__ __align__(8) uint64_t s_fullb[16];   // B slots: TMA expect_tx
+  __shared__ __align__(8) uint64_t s_emptyb[16];
   __shared__ __align__(8) uint64_t s_acc;
   __shared__ uint32_t s_tmem;
   __shared__ uint32_t s_active[4];
@@ -175,8 +179,8 @@ __global__ void __launch_bounds__(kThreads2) gather_gemm_tc2_kernel(
     // Completion of a stage is signalled by the copy engine itself
     // (cp.async.mbarrier.arrive.noinc: the arrive fires when this thread's prior cp.asyncs have
     // landed), so the gather warps never wait on their own loads: the only blocking point is
-    // a full ring.  (v1 waited with cp.async.wait_group + fence.proxy.async per stage, which
-    // exposed the full gather latency once per stage - see profiles/.)
+    // a full ring.  (Measured alternatives, profiles/: per-stage cp.async.wait_group + one
+    // arrive per warp is ~25 % slower.)
     Ring ring(S);
     const int64_t my_row = row0 + warp * 32 + lane;
     int32_t nxt = any ? load_src(p, k_first, my_row) : -1;
@@ -236,14 +240,15 @@ __global__ void __launch_bounds__(kThreads2) gather_gemm_tc2_kernel(
       const int kn = next_active(amask, k, p.kvol);
       const int n_chunks = p.n64 + p.tail32;
       for (int c = 0; c < n_chunks; ++c) {
-        mbar_wait(smem_u32(&s_fullb[rb.s]), rb.wraps & 1);
-        mbar_wait(smem_u32(&s_full[ring.s]), ring.wraps & 1);
-        fence_proxy_async();       // gathered rows were written through the generic proxy
-        tc_fence_after();
         if (lane == 0) {
+          mbar_wait(smem_u32(&s_fullb[rb.s]), rb.wraps & 1);
+          mbar_wait(smem_u32(&s_full[ring.s]), ring.wraps & 1);
+          if (p.consumer_fence) fence_proxy_async();   // off by default, see launch_gather_gemm_tc2
+          tc_fence_after();
           const uint32_t a_base = smem_base + ring.s * kABytes;
           const uint32_t b_base = smem_b + rb.s * p.b_stride;
-          if (c < p.n64) {
+          if (p.dbg & 8) {
+          } else if (c < p.n64) {
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const uint64_t ad = make_desc<128>(a_base + kk * 32);
@@ -264,9 +269,15 @@ __global__ void __launch_bounds__(kThreads2) gather_gemm_tc2_kernel(
               acc_flag = 1;
             }
           }
-          umma_commit(smem_u32(&s_empty[ring.s]));
-          umma_commit(smem_u32(&s_emptyb[rb.s]));
-          if (kn >= p.kvol && c == n_chunks - 1) umma_commit(smem_u32(&s_acc));
+          if (p.dbg & 16) {
+            mbar_arrive(smem_u32(&s_empty[ring.s]));
+            mbar_arrive(smem_u32(&s_emptyb[rb.s]));
+            if (kn >= p.kvol && c == n_chunks - 1) mbar_arrive(smem_u32(&s_acc));
+          } else {
+            umma_commit(smem_u32(&s_empty[ring.s]));
+            umma_commit(smem_u32(&s_emptyb[rb.s]));
+            if (kn >= p.kvol && c == n_chunks - 1) umma_commit(smem_u32(&s_acc));
+          }
         }
         __syncwarp();
         ring.advance();
@@ -287,11 +298,15 @@ __global__ void __launch_bounds__(kThreads2) gather_gemm_tc2_kernel(
           const uint32_t b_base = smem_b + ring.s * p.b_stride;
           const bool wide = c < p.n64;
           const int rowb = wide ? 128 : 64;
-          mbar_arrive_expect_tx(bar, (uint32_t)(p.c_res * rowb));
-          const CUtensorMap* tm = wide ? &tm64 : &tm32;
-          const int col = wide ? c * 64 : p.n64 * 64;
-          tma_load_2d(b_base, tm, col, k * p.c_res, bar);
-          if (n_half != p.c_res) tma_load_2d(b_base + n_half * rowb, tm, col, k * p.c_res + n_half, bar);
+          if (p.dbg & 4) {
+            mbar_arrive(bar);
+          } else {
+            mbar_arrive_expect_tx(bar, (uint32_t)(p.c_res * rowb));
+            const CUtensorMap* tm = wide ? &tm64 : &tm32;
+            const int col = wide ? c * 64 : p.n64 * 64;
+            tma_load_2d(b_base, tm, col, k * p.c_res, bar);
+            if (n_half != p.c_res) tma_load_2d(b_base + n_half * rowb, tm, col, k * p.c_res + n_half, bar);
+          }
           ring.advance();
         }
       }
@@ -387,11 +402,25 @@ int launch_gather_gemm_tc2(const void* in, const void* wt, int k, int c_red, int
     }
     if (p.sa > 8) p.sa = 8;
   }
+  // The gathered rows are written by cp.async (LDGSTS) and completion reaches the MMA warp through
+  // cp.async.mbarrier.arrive + mbarrier wait - the same hand-off CUTLASS's sm100 cp.async/UMMA
+  // mainloop uses, without a proxy fence.  A per-stage fence.proxy.async in the MMA warp costs
+  // ~1 us per stage (measured) and is therefore only available for A/B debugging.
+  p.consumer_fence = 0;
+  p.dbg = 0;
+  {
+    const char* ed = getenv("B2S_TC_DBG");
+    if (ed) p.dbg = atoi(ed);
+  }
+  {
+    const char* ef = getenv("B2S_TC_FENCE");
+    if (ef && ef[0] == '1') p.consumer_fence = 1;
+  }
   {  // tuning overrides (microbenchmarks only)
     const char* ea = getenv("B2S_TC_SA");
     const char* eb = getenv("B2S_TC_SB");
     if (ea && atoi(ea) >= 2 && atoi(ea) <= 8) p.sa = atoi(ea);
-    if (eb && atoi(eb) >= 1 && atoi(eb) <= 4) p.sb = atoi(eb);
+    if (eb && atoi(eb) >= 1 && atoi(eb) <= 16) p.sb = atoi(eb);
     while ((size_t)p.sa * kABytes + (size_t)p.sb * p.b_stride + 1024 > (size_t)budget1 && p.sa > 2) --p.sa;
   }
   B2S_REQUIRE(p.sa >= 2, B2S_ERR_UNSUPPORTED, "b2s_conv_gather_gemm: tile does not fit (C=%d)", c_res);

@@ -1,0 +1,426 @@
+// Sparse convolution gather-GEMM, tensor-core family, revision 3: PERSISTENT CTAs (fp16, sm_100a).
+//
+// Why (ablation of revision 2, profiles/r1_conv_ablation.txt): with copies, TMA and MMAs all
+// switched off, the v2 kernel still needed ~2/3 of its time - ~10 us of fixed cost per 128-row
+// tile (CTA launch, barrier init, TMEM alloc, mask scan, epilogue, TMEM free, exit) and ~440
+// cycles of mbarrier hand-shakes per pipeline stage in the single MMA-issuing thread (two waits
+// + two commits).  Revision 3 removes both:
+//
+//   * one CTA per SM slot loops over tiles (static stride); barriers and TMEM are set up once;
+//   * the accumulator is double-buffered in TMEM (2 x C_res columns) and drained by four
+//     dedicated epilogue warps, so the epilogue of tile i overlaps the main loop of tile i+1;
+//   * one "full" barrier per stage (128 gather arrivals + the TMA transaction bytes) and one
+//     "empty" barrier (one tcgen05.commit): the MMA thread does 1 wait + 1 commit per stage.
+//
+// Warp roles (10 warps): 0-3 gather producers (cp.async 16 B, zero-fill, SW128 / SW64 tiles),
+// 4 MMA issuer (+ TMEM alloc), 5 TMA weight-tile producer, 6-9 epilogue (TMEM -> fp16 rows).
+// Requires the per-tile active-offset masks that b2s_kmap_build emits.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "tc_common.cuh"
+
+namespace b2s {
+namespace tc3 {
+using namespace tc;
+
+constexpr int kThreads3 = 320;
+constexpr int kABytes = kTileM * 128;
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(tm), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+struct Params {
+  const __half* in;           // [n_src, c_red]
+  const int32_t* nbr;         // [K][n_rows]
+  const uint32_t* tile_mask;  // [tiles][ceil(K/32)]
+  const __half* bias;         // [c_res] or nullptr
+  __half* out;                // [n_rows, c_res]
+  int64_t n_rows;
+  int n_tiles;
+  int kvol, c_red, c_res, flip_k;
+  int n64, tail32;            // c_red = 64 * n64 + 32 * tail32
+  int stages, stage_stride;   // ring of (A tile, weight tile) pairs
+  int acc_stride, acc_bufs;   // TMEM columns per accumulator, 1 or 2 accumulators
+  int tmem_cols;
+};
+
+struct Ring {
+  int s = 0, wraps = 0, S;
+  __device__ explicit Ring(int stages) : S(stages) {}
+  __device__ __forceinline__ void advance() {
+    if (++s == S) {
+      s = 0;
+      ++wraps;
+    }
+  }
+};
+
+// active-offset bits of one tile (K <= 128), in the iteration order of this launch
+struct KMask {
+  uint32_t w0, w1, w2, w3;
+  __device__ __forceinline__ bool any() const { return (w0 | w1 | w2 | w3) != 0; }
+};
+__device__ __forceinline__ int first_above(uint32_t bits, int lo) {
+  if (lo >= 32) return -1;
+  if (lo > 0) bits &= 0xFFFFFFFFu << lo;
+  return bits ? __ffs(bits) - 1 : -1;
+}
+__device__ __forceinline__ int next_active(const KMask& m, int k, int kvol) {
+  int b;
+  if ((b = first_above(m.w0, k + 1)) >= 0) return b;
+  if (kvol > 32 && (b = first_above(m.w1, k + 1 - 32)) >= 0) return 32 + b;
+  if (kvol > 64 && (b = first_above(m.w2, k + 1 - 64)) >= 0) return 64 + b;
+  if (kvol > 96 && (b = first_above(m.w3, k + 1 - 96)) >= 0) return 96 + b;
+  return kvol;
+}
+__device__ __forceinline__ KMask load_mask(const Params& p, int tile) {
+  const int words = (p.kvol + 31) >> 5;
+  const uint32_t* tm = p.tile_mask + (int64_t)tile * words;
+  KMask m = {__ldg(tm), 0u, 0u, 0u};
+  if (words > 1) m.w1 = __ldg(tm + 1);
+  if (words > 2) m.w2 = __ldg(tm + 2);
+  if (words > 3) m.w3 = __ldg(tm + 3);
+  if (p.flip_k) {                      // bit k of the flipped mask = bit K-1-k of the stored one
+    if (p.kvol <= 32) {
+      m.w0 = __brev(m.w0) >> (32 - p.kvol);
+    } else {
+      KMask r = {0u, 0u, 0u, 0u};
+      for (int k = 0; k < p.kvol; ++k) {
+        const int kk = p.kvol - 1 - k;
+        const uint32_t src = kk < 32 ? m.w0 : kk < 64 ? m.w1 : kk < 96 ? m.w2 : m.w3;
+        if ((src >> (kk & 31)) & 1u) {
+          const uint32_t bit = 1u << (k & 31);
+          if (k < 32) r.w0 |= bit; else if (k < 64) r.w1 |= bit; else if (k < 96) r.w2 |= bit; else r.w3 |= bit;
+        }
+      }
+      m = r;
+    }
+  }
+  return m;
+}
+
+template <int ROWB>
+__device__ __forceinline__ void gather_chunk(const Params& p, int32_t my_src, uint32_t a_base,
+                                             int col0, int warp, int lane) {
+  constexpr int CH = ROWB / 16, RPI = 32 / CH;
+  const int sub = lane / CH, chunk = lane % CH;
+  const __half* base = p.in + col0 + chunk * 8;
+#pragma unroll
+  for (int i = 0; i < CH; ++i) {
+    const int rl = i * RPI + sub;
+    const int32_t src = __shfl_sync(0xffffffffu, my_src, rl);
+    const __half* g = src >= 0 ? base + (int64_t)src * p.c_red : p.in;
+    cp_async16(a_base + swz<ROWB>(warp * 32 + rl, chunk), g, src >= 0 ? 16u : 0u);
+  }
+}
+
+__device__ __forceinline__ int32_t load_src(const Params& p, int k, int64_t r) {
+  if (r >= p.n_rows) return -1;
+  return __ldg(p.nbr + (int64_t)(p.flip_k ? p.kvol - 1 - k : k) * p.n_rows + r);
+}
+
+__global__ void __launch_bounds__(kThreads3) gather_gemm_tc3_kernel(
+    const Params p, const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm32) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ __align__(8) uint64_t s_full[8];
+  __shared__ __align__(8) uint64_t s_empty[8];
+  __shared__ __align__(8) uint64_t s_acc_full[2];
+  __shared__ __align__(8) uint64_t s_acc_empty[2];
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = p.stages;
+  const int n_chunks = p.n64 + p.tail32;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(smem_u32(&s_full[s]), kProducerThreads + 1);   // 128 gather threads + TMA expect_tx
+      mbar_init(smem_u32(&s_empty[s]), 1);                     // one tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&s_acc_full[a]), 1);                  // tcgen05.commit after the last stage
+      mbar_init(smem_u32(&s_acc_empty[a]), 4);                 // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) tmem_alloc(smem_u32(&s_tmem), (uint32_t)p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  if (warp < 4) {
+    // ================================================================ A producers
+    Ring ring(S);
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const KMask amask = load_mask(p, tile);
+      const int64_t my_row = (int64_t)tile * kTileM + warp * 32 + lane;
+      int k = next_active(amask, -1, p.kvol);
+      int32_t nxt = k < p.kvol ? load_src(p, k, my_row) : -1;
+      while (k < p.kvol) {
+        const int32_t src = nxt;
+        const int kn = next_active(amask, k, p.kvol);
+        if (kn < p.kvol) nxt = load_src(p, kn, my_row);        // prefetch the next offset's map
+        for (int c = 0; c < n_chunks; ++c) {
+          if (ring.wraps > 0) mbar_wait(smem_u32(&s_empty[ring.s]), (ring.wraps - 1) & 1);
+          const uint32_t a_base = smem_base + ring.s * p.stage_stride;
+          if (c < p.n64) gather_chunk<128>(p, src, a_base, c * 64, warp, lane);
+          else gather_chunk<64>(p, src, a_base, p.n64 * 64, warp, lane);
+          cp_async_mbar_arrive_noinc(smem_u32(&s_full[ring.s]));
+          ring.advance();
+        }
+        k = kn;
+      }
+    }
+    cp_async_wait<0>();
+  } else if (warp == 4) {
+    // ================================================================= MMA issuer
+    if (lane == 0) {
+      const int n_half = p.c_res > 256 ? p.c_res / 2 : p.c_res;
+      const uint32_t idesc = make_idesc(n_half);
+      Ring ring(S);
+      int used = 0;                                     // non-empty tiles so far (accumulator turn)
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const KMask amask = load_mask(p, tile);
+        if (!amask.any()) continue;
+        const int ab = p.acc_bufs == 2 ? (used & 1) : 0;
+        const int turn = p.acc_bufs == 2 ? (used >> 1) : used;   // uses of this accumulator before
+        if (turn > 0) mbar_wait(smem_u32(&s_acc_empty[ab]), (turn - 1) & 1);
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(ab * p.acc_stride);
+        uint32_t acc_flag = 0;
+        for (int k = next_active(amask, -1, p.kvol); k < p.kvol; k = next_active(amask, k, p.kvol)) {
+          for (int c = 0; c < n_chunks; ++c) {
+            mbar_wait(smem_u32(&s_full[ring.s]), ring.wraps & 1);
+            tc_fence_after();
+            const uint32_t a_base = smem_base + ring.s * p.stage_stride;
+            const uint32_t b_base = a_base + kABytes;
+            if (c < p.n64) {
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint64_t ad = make_desc<128>(a_base + kk * 32);
+                umma_f16(tmem_acc, ad, make_desc<128>(b_base + kk * 32), idesc, acc_flag);
+                if (n_half != p.c_res)
+                  umma_f16(tmem_acc + (uint32_t)n_half, ad,
+                           make_desc<128>(b_base + n_half * 128 + kk * 32), idesc, acc_flag);
+                acc_flag = 1;
+              }
+            } else {
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk) {
+                const uint64_t ad = make_desc<64>(a_base + kk * 32);
+                umma_f16(tmem_acc, ad, make_desc<64>(b_base + kk * 32), idesc, acc_flag);
+                if (n_half != p.c_res)
+                  umma_f16(tmem_acc + (uint32_t)n_half, ad,
+                           make_desc<64>(b_base + n_half * 64 + kk * 32), idesc, acc_flag);
+                acc_flag = 1;
+              }
+            }
+            umma_commit(smem_u32(&s_empty[ring.s]));     // frees the stage when these MMAs retire
+            ring.advance();
+          }
+        }
+        umma_commit(smem_u32(&s_acc_full[ab]));          // accumulator complete -> epilogue
+        ++used;
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 5) {
+    // ================================================ B producer (TMA weight tiles)
+    if (lane == 0) {
+      const int n_half = p.c_res > 256 ? p.c_res / 2 : p.c_res;
+      Ring ring(S);
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const KMask amask = load_mask(p, tile);
+        for (int k = next_active(amask, -1, p.kvol); k < p.kvol; k = next_active(amask, k, p.kvol)) {
+          for (int c = 0; c < n_chunks; ++c) {
+            if (ring.wraps > 0) mbar_wait(smem_u32(&s_empty[ring.s]), (ring.wraps - 1) & 1);
+            const uint32_t bar = smem_u32(&s_full[ring.s]);
+            const uint32_t b_base = smem_base + ring.s * p.stage_stride + kABytes;
+            const bool wide = c < p.n64;
+            const int rowb = wide ? 128 : 64;
+            mbar_arrive_expect_tx(bar, (uint32_t)(p.c_res * rowb));
+            const CUtensorMap* tm = wide ? &tm64 : &tm32;
+            const int col = wide ? c * 64 : p.n64 * 64;
+            tma_load_2d(b_base, tm, col, k * p.c_res, bar);
+            if (n_half != p.c_res) tma_load_2d(b_base + n_half * rowb, tm, col, k * p.c_res + n_half, bar);
+            ring.advance();
+          }
+        }
+      }
+    }
+  } else {
+    // =================================================================== epilogue
+    const int q = warp & 3;                              // TMEM lane quarter this warp may read
+    int used = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const KMask amask = load_mask(p, tile);
+      const bool any = amask.any();
+      const int ab = p.acc_bufs == 2 ? (used & 1) : 0;
+      const int turn = p.acc_bufs == 2 ? (used >> 1) : used;
+      if (any) {
+        mbar_wait(smem_u32(&s_acc_full[ab]), turn & 1);
+        tc_fence_after();
+      }
+      const int64_t r = (int64_t)tile * kTileM + q * 32 + lane;
+      const uint32_t t_lane = tmem_base + (uint32_t)(ab * p.acc_stride) + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < p.c_res; c0 += 16) {
+        uint32_t v[16];
+        if (any) {
+          tmem_ld16(t_lane + (uint32_t)c0, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0u;
+        }
+        if (r < p.n_rows) {
+          __align__(16) __half h[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float f = __uint_as_float(v[j]);
+            if (p.bias) f += __half2float(__ldg(p.bias + c0 + j));
+            h[j] = __float2half_rn(f);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(p.out + r * p.c_res + c0);
+          dst[0] = reinterpret_cast<const uint4*>(h)[0];
+          dst[1] = reinterpret_cast<const uint4*>(h)[1];
+        }
+      }
+      if (any) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s_acc_empty[ab]));   // accumulator may be overwritten
+        ++used;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+static bool make_weight_map(CUtensorMap* tm, const void* w, int k, int c_res, int c_red, int box_cols,
+                            int box_rows) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)c_red, (cuuint64_t)k * c_res};
+  cuuint64_t strides[1] = {(cuuint64_t)c_red * sizeof(__half)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace tc3
+
+// wt: [K][c_res][c_red] fp16 (K-major B operand); nbr and tile_mask must be non-null
+int launch_gather_gemm_tc3(const void* in, const void* wt, int k, int c_red, int c_res, int flip_k,
+                           const int32_t* nbr, const uint32_t* tile_mask, int64_t n_rows,
+                           const void* bias, void* out, cudaStream_t st) {
+  using namespace tc3;
+  Params p;
+  p.in = reinterpret_cast<const __half*>(in);
+  p.nbr = nbr;
+  p.tile_mask = tile_mask;
+  p.bias = reinterpret_cast<const __half*>(bias);
+  p.out = reinterpret_cast<__half*>(out);
+  p.n_rows = n_rows;
+  p.n_tiles = (int)ceil_div(n_rows, kTileM);
+  p.kvol = k;
+  p.c_red = c_red;
+  p.c_res = c_res;
+  p.flip_k = flip_k;
+  p.n64 = c_red / 64;
+  p.tail32 = (c_red % 64) ? 1 : 0;
+  const int n_half = c_res > 256 ? c_res / 2 : c_res;
+  CUtensorMap tm64, tm32;
+  memset(&tm64, 0, sizeof(tm64));
+  memset(&tm32, 0, sizeof(tm32));
+  if (p.n64) B2S_REQUIRE(make_weight_map(&tm64, wt, k, c_res, c_red, 64, n_half), B2S_ERR_CUDA,
+                         "b2s_conv_gather_gemm: cuTensorMapEncodeTiled failed (64-wide)");
+  if (p.tail32) B2S_REQUIRE(make_weight_map(&tm32, wt, k, c_res, c_red, 32, n_half), B2S_ERR_CUDA,
+                            "b2s_conv_gather_gemm: cuTensorMapEncodeTiled failed (32-wide)");
+  // accumulator layout in TMEM: power-of-two stride per accumulator, two of them when they fit
+  int stride = 32;
+  while (stride < c_res) stride <<= 1;
+  p.acc_stride = stride;
+  p.acc_bufs = 2 * stride <= 512 ? 2 : 1;
+  p.tmem_cols = stride * p.acc_bufs;
+  const int rowb_max = p.n64 ? 128 : 64;
+  p.stage_stride = (kABytes + ((c_res + 7) / 8) * 8 * rowb_max + 1023) & ~1023;
+  // two CTAs per SM when both the ring (>= 3 stages) and the TMEM columns fit twice
+  const int budget2 = 111 * 1024, budget1 = 222 * 1024;
+  int ctas_per_sm = 1;
+  int stages = budget2 / p.stage_stride;
+  if (stages >= 3 && p.tmem_cols <= 256) {
+    ctas_per_sm = 2;
+  } else {
+    stages = budget1 / p.stage_stride;
+  }
+  if (stages > 8) stages = 8;
+  {
+    const char* es = getenv("B2S_TC_STAGES");
+    if (es && atoi(es) >= 2 && atoi(es) <= 8 && atoi(es) * p.stage_stride <= budget1) {
+      stages = atoi(es);
+      ctas_per_sm = (stages * p.stage_stride <= budget2 && p.tmem_cols <= 256) ? 2 : 1;
+    }
+  }
+  B2S_REQUIRE(stages >= 2, B2S_ERR_UNSUPPORTED, "b2s_conv_gather_gemm: tile does not fit (C=%d)", c_res);
+  p.stages = stages;
+  const size_t smem = (size_t)stages * p.stage_stride + 1024;
+  static size_t smem_opt_in = 0;
+  if (smem > smem_opt_in) {
+    cudaError_t e = cudaFuncSetAttribute(gather_gemm_tc3_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    B2S_REQUIRE(e == cudaSuccess, B2S_ERR_CUDA, "b2s_conv_gather_gemm: cannot opt in to %zu B smem: %s",
+                smem, cudaGetErrorString(e));
+    smem_opt_in = smem;
+  }
+  int grid = sm_count() * ctas_per_sm;
+  if (grid > p.n_tiles) grid = p.n_tiles;
+  gather_gemm_tc3_kernel<<<grid, kThreads3, smem, st>>>(p, tm64, tm32);
+  return B2S_OK;
+}
+
+}  // namespace b2s
