@@ -116,6 +116,9 @@ int b2s_kmap_build(const int32_t* in_coords, int64_t n_in, const int32_t* out_co
                    uint32_t* tile_mask_in, void* ws, size_t ws_bytes, b2s_stream_t stream);
 int b2s_kmap_pairs(const int32_t* nbr_out, int32_t k, int64_t n_out, int32_t* nbmaps,
                    int64_t* d_total, void* ws, size_t ws_bytes, b2s_stream_t stream);
+/* active-offset masks of the 128-row tiles of an arbitrary gather map nbr [K, n] (e.g. a
+ * column-permuted copy of nbr_out): tile_mask uint32 [ceil(n/128)][ceil(K/32)].           */
+int b2s_tile_mask(const int32_t* nbr, int32_t k, int64_t n, uint32_t* tile_mask, b2s_stream_t stream);
 
 /* ------------------------------------------------------------ convolution ---
  * replaces convolution_forward_cuda / convolution_backward_cuda
@@ -128,7 +131,10 @@ int b2s_kmap_pairs(const int32_t* nbr_out, int32_t k, int64_t n_out, int32_t* nb
  *   (input gradient: c_red = c_out, c_res = c_in).  fp32 accumulation over all
  *   offsets, one write per output row, no atomics, deterministic.
  *   `in` has n_src rows of c_red channels; `out` n_rows x c_res; optional bias[c_res];
- *   optional tile_mask = the b2s_kmap_build mask that belongs to `nbr` (NULL: scanned).
+ *   optional tile_mask = the b2s_kmap_build / b2s_tile_mask mask that belongs to `nbr` (NULL:
+ *   scanned); optional row_perm int32 [n_rows]: result row j of the launch is written to
+ *   out[row_perm[j]] - lets the caller group rows with similar neighbourhoods into the same
+ *   128-row tile (column j of `nbr` then describes original row row_perm[j]).
  * b2s_conv_wgrad: grad_w[k] = sum over pairs of offset k of in[i]^T * grad_out[o],
  *   pairs from b2s_kmap_pairs (device-resident sizes, no host sync).  grad_w is
  *   fp32 [K, c_in, c_out] and is zero-filled by the call.
@@ -139,8 +145,8 @@ size_t b2s_conv_workspace_bytes(int32_t dtype, int64_t n_rows, int32_t c_in, int
 int b2s_conv_gather_gemm(int32_t dtype, const void* in, int64_t n_src, const void* weight,
                          int32_t k, int32_t c_in, int32_t c_out, int32_t transpose_w,
                          int32_t flip_k, const int32_t* nbr, const uint32_t* tile_mask,
-                         int64_t n_rows, const void* bias, void* out, void* ws, size_t ws_bytes,
-                         b2s_stream_t stream);
+                         const int32_t* row_perm, int64_t n_rows, const void* bias, void* out,
+                         void* ws, size_t ws_bytes, b2s_stream_t stream);
 int b2s_conv_wgrad(int32_t dtype, const void* in, int64_t n_in, const void* grad_out,
                    int64_t n_out, int32_t k, int32_t c_in, int32_t c_out, const int32_t* nbmaps,
                    const int32_t* nbsizes, int32_t swap_pairs, float* grad_w, void* ws,

@@ -22,11 +22,7 @@ F32, F16 = 0, 1
 # ---- measurement hooks (bench.py): count of libb2s kernel launches and optional per-call
 # CUDA-event timing of the convolution kernels.  Off the hot path unless PROFILER is set.
 STATS = {"launches": 0}
-PROFILER = None          # object with .record(kind, meta, start_event, end_event)
-
-
-def _launched(n: int = 1) -> None:
-    STATS["launches"] += n
+PROFILER = None          # object with .event() -> cuda Event and .record(kind, meta, start, end)
 
 
 class _Timed:
@@ -39,13 +35,13 @@ class _Timed:
 
     def __enter__(self):
         if PROFILER is not None:
-            self.start = torch.cuda.Event(enable_timing=True)
+            self.start = PROFILER.event()
             self.start.record()
         return self
 
     def __exit__(self, *exc):
         if self.start is not None:
-            end = torch.cuda.Event(enable_timing=True)
+            end = PROFILER.event()
             end.record()
             PROFILER.record(self.kind, self.meta, self.start, end)
         return False
@@ -232,6 +228,16 @@ def kmap_build(in_coords: torch.Tensor, out_coords: torch.Tensor, offsets: torch
     return nbr_out, nbr_in, nbsizes, mask_out, mask_in
 
 
+def tile_mask(nbr: torch.Tensor) -> torch.Tensor:
+    """Active-offset bits per 128-row tile of a gather map [K, n] (b2s_tile_mask)."""
+    _cuda(nbr)
+    nbr = nbr.contiguous()
+    k, n = nbr.shape
+    mask = torch.empty((max((n + 127) // 128, 1), (k + 31) // 32), dtype=torch.int32, device=nbr.device)
+    check(_lib.lib().b2s_tile_mask(nbr.data_ptr(), k, n, mask.data_ptr(), _stream()), "tile_mask")
+    return mask
+
+
 def kmap_pairs(nbr_out: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """(pairs int32 [K*N_out, 2] padded buffer, d_total int64 [1]) - reference pair order."""
     _cuda(nbr_out)
@@ -251,7 +257,8 @@ def kmap_pairs(nbr_out: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 def conv_gather_gemm(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Tensor],
                      n_rows: int, transpose_w: bool, flip_k: bool,
                      bias: Optional[torch.Tensor] = None, pairs_hint=None,
-                     tile_mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+                     tile_mask: Optional[torch.Tensor] = None,
+                     row_perm: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[r] = sum_k feats[nbr[k'][r]] @ (W[k] or W[k]^T); see b2s_conv_gather_gemm."""
     _cuda(feats, weight, nbr, bias)
     feats, weight = feats.contiguous(), weight.contiguous()
@@ -277,9 +284,9 @@ def conv_gather_gemm(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[to
     with _Timed("dgrad" if transpose_w else "fwd",
                 {"k": k, "c_in": c_in, "c_out": c_out, "rows": n_rows, "dtype": code, "pairs": pairs_hint}):
         check(L.b2s_conv_gather_gemm(code, feats.data_ptr(), feats.shape[0], weight.data_ptr(), k, c_in,
-                                     c_out, int(transpose_w), int(flip_k), _ptr(nbr), _ptr(tile_mask), n_rows,
-                                     _ptr(bias), out.data_ptr(), _ptr(ws), nbytes, _stream()),
-              "conv_gather_gemm")
+                                     c_out, int(transpose_w), int(flip_k), _ptr(nbr), _ptr(tile_mask),
+                                     _ptr(row_perm), n_rows, _ptr(bias), out.data_ptr(), _ptr(ws), nbytes,
+                                     _stream()), "conv_gather_gemm")
     return out
 
 

@@ -7,8 +7,8 @@
 namespace b2s {
 template <typename T>
 int launch_gather_gemm_simt(const void* in, const void* weight, int k, int c_in, int c_out,
-                            int transpose_w, int flip_k, const int32_t* nbr, int64_t n_rows,
-                            const void* bias, void* out, cudaStream_t st);
+                            int transpose_w, int flip_k, const int32_t* nbr, const int32_t* row_perm,
+                            int64_t n_rows, const void* bias, void* out, cudaStream_t st);
 template <typename T>
 int launch_wgrad_simt(const void* in, const void* gout, const int32_t* nbmaps,
                       const int32_t* nbsizes, int64_t n_identity, int64_t n_pairs_bound, int k,
@@ -18,8 +18,8 @@ int launch_wgrad_simt(const void* in, const void* gout, const int32_t* nbmaps,
 bool tc_gather_gemm_supported(int c_red, int c_res);
 int launch_gather_gemm_tc(const void* in, const void* weight, int k, int c_in, int c_out,
                           int transpose_w, int flip_k, const int32_t* nbr, const uint32_t* tile_mask,
-                          int64_t n_rows, const void* bias, void* out, void* ws, size_t ws_bytes,
-                          cudaStream_t st);
+                          const int32_t* row_perm, int64_t n_rows, const void* bias, void* out, void* ws,
+                          size_t ws_bytes, cudaStream_t st);
 size_t tc_gather_gemm_workspace(int k, int c_in, int c_out);
 bool tc_wgrad_supported(int c_in, int c_out);
 int launch_wgrad_tc(const void* in, const void* gout, const int32_t* nbmaps,
@@ -50,14 +50,15 @@ size_t b2s_conv_workspace_bytes(int32_t dtype, int64_t n_rows, int32_t c_in, int
 int b2s_conv_gather_gemm(int32_t dtype, const void* in, int64_t n_src, const void* weight,
                          int32_t k, int32_t c_in, int32_t c_out, int32_t transpose_w,
                          int32_t flip_k, const int32_t* nbr, const uint32_t* tile_mask,
-                         int64_t n_rows, const void* bias, void* out, void* ws, size_t ws_bytes,
-                         b2s_stream_t stream) {
+                         const int32_t* row_perm, int64_t n_rows, const void* bias, void* out, void* ws,
+                         size_t ws_bytes, b2s_stream_t stream) {
   B2S_REQUIRE(dtype == B2S_F32 || dtype == B2S_F16, B2S_ERR_INVALID, "b2s_conv_gather_gemm: dtype");
   B2S_REQUIRE(k >= 1 && c_in >= 1 && c_out >= 1 && n_rows >= 0 && n_src >= 0, B2S_ERR_INVALID,
               "b2s_conv_gather_gemm: bad sizes");
   if (n_rows == 0) return B2S_OK;
   B2S_REQUIRE(nbr || k == 1, B2S_ERR_INVALID,
               "b2s_conv_gather_gemm: nbr == NULL (identity map) needs k == 1");
+  B2S_REQUIRE(nbr || !row_perm, B2S_ERR_INVALID, "b2s_conv_gather_gemm: row_perm needs a gather map");
   B2S_REQUIRE(nbr || n_rows <= n_src, B2S_ERR_INVALID,
               "b2s_conv_gather_gemm: identity map with n_rows > n_src");
   B2S_REQUIRE(in && weight && out, B2S_ERR_INVALID, "b2s_conv_gather_gemm: null pointer");
@@ -69,14 +70,14 @@ int b2s_conv_gather_gemm(int32_t dtype, const void* in, int64_t n_src, const voi
                          reinterpret_cast<uintptr_t>(out)) & 15) == 0;
   if (dtype == B2S_F16 && !force_simt() && aligned && tc_gather_gemm_supported(c_red, c_res)) {
     int rc = launch_gather_gemm_tc(in, weight, k, c_in, c_out, transpose_w, flip_k, nbr, tile_mask,
-                                   n_rows, bias, out, ws, ws_bytes, st);
+                                   row_perm, n_rows, bias, out, ws, ws_bytes, st);
     if (rc != B2S_OK) return rc;
   } else if (dtype == B2S_F16) {
-    launch_gather_gemm_simt<__half>(in, weight, k, c_in, c_out, transpose_w, flip_k, nbr, n_rows,
-                                    bias, out, st);
+    launch_gather_gemm_simt<__half>(in, weight, k, c_in, c_out, transpose_w, flip_k, nbr, row_perm,
+                                    n_rows, bias, out, st);
   } else {
-    launch_gather_gemm_simt<float>(in, weight, k, c_in, c_out, transpose_w, flip_k, nbr, n_rows,
-                                   bias, out, st);
+    launch_gather_gemm_simt<float>(in, weight, k, c_in, c_out, transpose_w, flip_k, nbr, row_perm,
+                                   n_rows, bias, out, st);
   }
   B2S_CHECK_LAUNCH("b2s_conv_gather_gemm");
   return B2S_OK;

@@ -19,8 +19,8 @@ constexpr int BM = 64, BN = 64, BK = 16;
 template <typename T>
 __global__ void __launch_bounds__(256) gather_gemm_simt_kernel(
     const T* __restrict__ in, const T* __restrict__ weight, const int32_t* __restrict__ nbr,
-    const T* __restrict__ bias, T* __restrict__ out, int64_t n_rows, int kvol, int c_in, int c_out,
-    int transpose_w, int flip_k) {
+    const int32_t* __restrict__ row_perm, const T* __restrict__ bias, T* __restrict__ out, int64_t n_rows,
+    int kvol, int c_in, int c_out, int transpose_w, int flip_k) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   __shared__ int32_t s_row[BM];
@@ -94,13 +94,14 @@ __global__ void __launch_bounds__(256) gather_gemm_simt_kernel(
   for (int i = 0; i < 4; ++i) {
     int64_t r = row0 + ty * 4 + i;
     if (r >= n_rows) continue;
+    const int64_t r_out = row_perm ? (int64_t)__ldg(row_perm + r) : r;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int n = col0 + tx * 4 + j;
       if (n < c_res) {
         float v = acc[i][j];
         if (bias) v += FeatIO<T>::load(bias + n);
-        FeatIO<T>::store(out + r * c_res + n, v);
+        FeatIO<T>::store(out + r_out * c_res + n, v);
       }
     }
   }
@@ -194,12 +195,12 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(
 
 template <typename T>
 int launch_gather_gemm_simt(const void* in, const void* weight, int k, int c_in, int c_out,
-                            int transpose_w, int flip_k, const int32_t* nbr, int64_t n_rows,
-                            const void* bias, void* out, cudaStream_t st) {
+                            int transpose_w, int flip_k, const int32_t* nbr, const int32_t* row_perm,
+                            int64_t n_rows, const void* bias, void* out, cudaStream_t st) {
   const int c_res = transpose_w ? c_in : c_out;
   dim3 grid((unsigned)ceil_div(n_rows, BM), (unsigned)ceil_div(c_res, BN));
   gather_gemm_simt_kernel<T><<<grid, 256, 0, st>>>(
-      reinterpret_cast<const T*>(in), reinterpret_cast<const T*>(weight), nbr,
+      reinterpret_cast<const T*>(in), reinterpret_cast<const T*>(weight), nbr, row_perm,
       reinterpret_cast<const T*>(bias), reinterpret_cast<T*>(out), n_rows, k, c_in, c_out,
       transpose_w, flip_k);
   return 0;
@@ -223,11 +224,11 @@ int launch_wgrad_simt(const void* in, const void* gout, const int32_t* nbmaps,
 }
 
 template int launch_gather_gemm_simt<float>(const void*, const void*, int, int, int, int, int,
-                                            const int32_t*, int64_t, const void*, void*,
-                                            cudaStream_t);
+                                            const int32_t*, const int32_t*, int64_t, const void*,
+                                            void*, cudaStream_t);
 template int launch_gather_gemm_simt<__half>(const void*, const void*, int, int, int, int, int,
-                                             const int32_t*, int64_t, const void*, void*,
-                                             cudaStream_t);
+                                             const int32_t*, const int32_t*, int64_t, const void*,
+                                             void*, cudaStream_t);
 template int launch_wgrad_simt<float>(const void*, const void*, const int32_t*, const int32_t*,
                                       int64_t, int64_t, int, int, int, int, float*, cudaStream_t);
 template int launch_wgrad_simt<__half>(const void*, const void*, const int32_t*, const int32_t*,

@@ -28,6 +28,7 @@ struct Params {
   const __half* in;     // [n_src, c_red]
   const __half* wt;     // [K][c_res][c_red]  (K-major B operand)
   const int32_t* nbr;   // [K][n_rows] or nullptr (identity, K == 1)
+  const int32_t* row_perm;  // out row of launch row j, or nullptr
   const __half* bias;   // [c_res] or nullptr
   __half* out;          // [n_rows, c_res]
   int64_t n_rows;
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(kThreads) gather_gemm_tc_kernel(const Params p
       tc_fence_after();
     }
     const int64_t r = row0 + warp * 32 + lane;
+    const int64_t r_out = (p.row_perm && r < p.n_rows) ? (int64_t)__ldg(p.row_perm + r) : r;
     const uint32_t t_lane = tmem_acc + ((uint32_t)(warp * 32) << 16);
     for (int c0 = 0; c0 < p.c_res; c0 += 16) {
       uint32_t v[16];
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(kThreads) gather_gemm_tc_kernel(const Params p
           if (p.bias) f += __half2float(__ldg(p.bias + c0 + j));
           h[j] = __float2half_rn(f);
         }
-        uint4* dst = reinterpret_cast<uint4*>(p.out + r * p.c_res + c0);
+        uint4* dst = reinterpret_cast<uint4*>(p.out + r_out * p.c_res + c0);
         dst[0] = reinterpret_cast<const uint4*>(h)[0];
         dst[1] = reinterpret_cast<const uint4*>(h)[1];
       }
@@ -232,12 +234,12 @@ static int tmem_cols_for(int n) {
 }  // namespace tc
 
 int launch_gather_gemm_tc2(const void* in, const void* wt, int k, int c_red, int c_res, int flip_k,
-                           const int32_t* nbr, const uint32_t* tile_mask, int64_t n_rows,
-                           const void* bias, void* out, cudaStream_t st);
+                           const int32_t* nbr, const uint32_t* tile_mask, const int32_t* row_perm,
+                           int64_t n_rows, const void* bias, void* out, cudaStream_t st);
 
 int launch_gather_gemm_tc3(const void* in, const void* wt, int k, int c_red, int c_res, int flip_k,
-                           const int32_t* nbr, const uint32_t* tile_mask, int64_t n_rows,
-                           const void* bias, void* out, cudaStream_t st);
+                           const int32_t* nbr, const uint32_t* tile_mask, const int32_t* row_perm,
+                           int64_t n_rows, const void* bias, void* out, cudaStream_t st);
 
 static bool use_v2() {
   static int v = -1;
@@ -270,8 +272,8 @@ size_t tc_gather_gemm_workspace(int k, int c_in, int c_out) {
 
 int launch_gather_gemm_tc(const void* in, const void* weight, int k, int c_in, int c_out,
                           int transpose_w, int flip_k, const int32_t* nbr, const uint32_t* tile_mask,
-                          int64_t n_rows, const void* bias, void* out, void* ws, size_t ws_bytes,
-                          cudaStream_t st) {
+                          const int32_t* row_perm, int64_t n_rows, const void* bias, void* out, void* ws,
+                          size_t ws_bytes, cudaStream_t st) {
   using namespace tc;
   const int c_red = transpose_w ? c_out : c_in, c_res = transpose_w ? c_in : c_out;
   const __half* wt = reinterpret_cast<const __half*>(weight);
@@ -285,15 +287,16 @@ int launch_gather_gemm_tc(const void* in, const void* weight, int k, int c_in, i
     wt = reinterpret_cast<const __half*>(ws);
   }  // input gradient: B_k[n = c_in][c = c_out] = W[k][n][c] is the stored layout already
   if (!use_v1() && !use_v2() && nbr && tile_mask)      // persistent kernel (needs the tile masks)
-    return launch_gather_gemm_tc3(in, wt, k, c_red, c_res, flip_k, nbr, tile_mask, n_rows, bias, out,
-                                  st);
+    return launch_gather_gemm_tc3(in, wt, k, c_red, c_res, flip_k, nbr, tile_mask, row_perm, n_rows, bias,
+                                  out, st);
   if (!use_v1())
-    return launch_gather_gemm_tc2(in, wt, k, c_red, c_res, flip_k, nbr, tile_mask, n_rows, bias, out,
-                                  st);
+    return launch_gather_gemm_tc2(in, wt, k, c_red, c_res, flip_k, nbr, tile_mask, row_perm, n_rows, bias,
+                                  out, st);
   Params p;
   p.in = reinterpret_cast<const __half*>(in);
   p.wt = wt;
   p.nbr = nbr;
+  p.row_perm = row_perm;
   p.bias = reinterpret_cast<const __half*>(bias);
   p.out = reinterpret_cast<__half*>(out);
   p.n_rows = n_rows;

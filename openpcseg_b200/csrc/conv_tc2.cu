@@ -50,6 +50,7 @@ struct Params {
   const __half* in;     // [n_src, c_red]
   const int32_t* nbr;   // [K][n_rows] or nullptr (identity, K == 1)
   const uint32_t* tile_mask;  // [tiles][ceil(K/32)] active-offset bits of nbr's tiles, or nullptr
+  const int32_t* row_perm;    // out row of launch row j, or nullptr
   const __half* bias;   // [c_res] or nullptr
   __half* out;          // [n_rows, c_res]
   int64_t n_rows;
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(kThreads2) gather_gemm_tc2_kernel(
       tc_fence_after();
     }
     const int64_t r = my_row;
+    const int64_t r_out = (p.row_perm && r < p.n_rows) ? (int64_t)__ldg(p.row_perm + r) : r;
     const uint32_t t_lane = tmem_acc + ((uint32_t)(warp * 32) << 16);
     for (int c0 = 0; c0 < p.c_res; c0 += 16) {
       uint32_t v[16];
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(kThreads2) gather_gemm_tc2_kernel(
           if (p.bias) f += __half2float(__ldg(p.bias + c0 + j));
           h[j] = __float2half_rn(f);
         }
-        uint4* dst = reinterpret_cast<uint4*>(p.out + r * p.c_res + c0);
+        uint4* dst = reinterpret_cast<uint4*>(p.out + r_out * p.c_res + c0);
         dst[0] = reinterpret_cast<const uint4*>(h)[0];
         dst[1] = reinterpret_cast<const uint4*>(h)[1];
       }
@@ -358,13 +360,14 @@ static bool make_weight_map(CUtensorMap* tm, const void* w, int k, int c_res, in
 
 // wt: [K][c_res][c_red] fp16 (K-major B operand), already transposed by the caller if needed
 int launch_gather_gemm_tc2(const void* in, const void* wt, int k, int c_red, int c_res, int flip_k,
-                           const int32_t* nbr, const uint32_t* tile_mask, int64_t n_rows,
-                           const void* bias, void* out, cudaStream_t st) {
+                           const int32_t* nbr, const uint32_t* tile_mask, const int32_t* row_perm,
+                           int64_t n_rows, const void* bias, void* out, cudaStream_t st) {
   using namespace tc2;
   Params p;
   p.in = reinterpret_cast<const __half*>(in);
   p.nbr = nbr;
   p.tile_mask = nbr ? tile_mask : nullptr;
+  p.row_perm = row_perm;
   p.bias = reinterpret_cast<const __half*>(bias);
   p.out = reinterpret_cast<__half*>(out);
   p.n_rows = n_rows;

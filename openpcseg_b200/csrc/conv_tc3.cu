@@ -12,7 +12,13 @@
 //   * one "full" barrier per stage (128 gather arrivals + the TMA transaction bytes) and one
 //     "empty" barrier (one tcgen05.commit): the MMA thread does 1 wait + 1 commit per stage.
 //
-// Warp roles (10 warps): 0-3 gather producers (cp.async 16 B, zero-fill, SW128 / SW64 tiles),
+// Revision 3b - weight reuse.  Measured on v3 (profiles/r1_conv_ablation.txt): every layer ran at
+// ~5.8-6.2 TB/s of L2->SM weight traffic (each 128-row tile re-streams all K weight slices), i.e.
+// the kernel was bound by L2 bandwidth on WEIGHTS, not by gathers or MMAs.  A CTA therefore owns
+// T = 2 row tiles (256 rows): one TMA weight tile per stage now feeds two MMAs (rows 0-127 and
+// 128-255, separate TMEM accumulators), halving the weight bytes per output row.
+//
+// Warp roles (6 + 4T warps): 0..4T-1 gather producers (cp.async 16 B, zero-fill, SW128 / SW64 tiles),
 // 4 MMA issuer (+ TMEM alloc), 5 TMA weight-tile producer, 6-9 epilogue (TMEM -> fp16 rows).
 // Requires the per-tile active-offset masks that b2s_kmap_build emits.
 #include <cuda.h>
@@ -25,7 +31,6 @@ namespace b2s {
 namespace tc3 {
 using namespace tc;
 
-constexpr int kThreads3 = 320;
 constexpr int kABytes = kTileM * 128;
 
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -44,14 +49,33 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+__device__ __forceinline__ void mbar_wait_backoff(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(256);
+  }
+}
+
 struct Params {
   const __half* in;           // [n_src, c_red]
   const int32_t* nbr;         // [K][n_rows]
   const uint32_t* tile_mask;  // [tiles][ceil(K/32)]
+  const int32_t* row_perm;    // out row of launch row j, or nullptr
   const __half* bias;         // [c_res] or nullptr
   __half* out;                // [n_rows, c_res]
   int64_t n_rows;
-  int n_tiles;
+  int n_tiles;                // CTA tiles (128*T rows each)
+  int n_tiles128;             // 128-row tiles (granularity of tile_mask)
   int kvol, c_red, c_res, flip_k;
   int n64, tail32;            // c_red = 64 * n64 + 32 * tail32
   int stages, stage_stride;   // ring of (A tile, weight tile) pairs
@@ -114,19 +138,64 @@ __device__ __forceinline__ KMask load_mask(const Params& p, int tile) {
   return m;
 }
 
-template <int ROWB>
-__device__ __forceinline__ void gather_chunk(const Params& p, int32_t my_src, uint32_t a_base,
-                                             int col0, int warp, int lane) {
-  constexpr int CH = ROWB / 16, RPI = 32 / CH;
-  const int sub = lane / CH, chunk = lane % CH;
-  const __half* base = p.in + col0 + chunk * 8;
+// Gather bookkeeping of one producer thread, set up ONCE per kernel offset and reused by every
+// channel chunk of that offset: the global row pointers of the rows this lane copies (8 row
+// slots for 128-byte tiles, 4 for the 64-byte tail tile), a bit per slot telling whether the
+// neighbour exists (missing ones are zero-filled by cp.async with src-size 0), and the constant
+// swizzled shared-memory offsets.  The per-stage work is then one add + one LDGSTS per slot - the
+// first persistent version recomputed shuffles and 64-bit address math per stage and was bound by
+// instruction issue in these four warps (profiles/r1_conv_ablation.txt).
+struct GatherSlots {
+  const __half* p128[8];
+  const __half* p64[4];
+  uint32_t off128[8];
+  uint32_t off64[4];
+  uint32_t ok128, ok64;
+};
+
+__device__ __forceinline__ void slots_init(GatherSlots& g, int warp, int lane) {
 #pragma unroll
-  for (int i = 0; i < CH; ++i) {
-    const int rl = i * RPI + sub;
-    const int32_t src = __shfl_sync(0xffffffffu, my_src, rl);
-    const __half* g = src >= 0 ? base + (int64_t)src * p.c_red : p.in;
-    cp_async16(a_base + swz<ROWB>(warp * 32 + rl, chunk), g, src >= 0 ? 16u : 0u);
+  for (int i = 0; i < 8; ++i) {
+    const int row = warp * 32 + i * 4 + (lane >> 3);          // 0 .. 128T-1
+    g.off128[i] = (uint32_t)(row >> 7) * kABytes + swz<128>(row & 127, lane & 7);
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = warp * 32 + i * 8 + (lane >> 2);
+    g.off64[i] = (uint32_t)(row >> 7) * kABytes + swz<64>(row & 127, lane & 3);
+  }
+}
+
+__device__ __forceinline__ void slots_set_rows(GatherSlots& g, const Params& p, int32_t my_src, int lane) {
+  g.ok128 = 0;
+  g.ok64 = 0;
+  if (p.n64) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int32_t src = __shfl_sync(0xffffffffu, my_src, i * 4 + (lane >> 3));
+      g.p128[i] = p.in + (src >= 0 ? (int64_t)src * p.c_red : 0) + (lane & 7) * 8;
+      g.ok128 |= (src >= 0 ? 1u : 0u) << i;
+    }
+  }
+  if (p.tail32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int32_t src = __shfl_sync(0xffffffffu, my_src, i * 8 + (lane >> 2));
+      g.p64[i] = p.in + (src >= 0 ? (int64_t)src * p.c_red : 0) + p.n64 * 64 + (lane & 3) * 8;
+      g.ok64 |= (src >= 0 ? 1u : 0u) << i;
+    }
+  }
+}
+
+__device__ __forceinline__ void gather_wide(const GatherSlots& g, uint32_t a_base, int col) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    cp_async16(a_base + g.off128[i], g.p128[i] + col, ((g.ok128 >> i) & 1u) ? 16u : 0u);
+}
+__device__ __forceinline__ void gather_tail(const GatherSlots& g, uint32_t a_base) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    cp_async16(a_base + g.off64[i], g.p64[i], ((g.ok64 >> i) & 1u) ? 16u : 0u);
 }
 
 __device__ __forceinline__ int32_t load_src(const Params& p, int k, int64_t r) {
@@ -134,8 +203,26 @@ __device__ __forceinline__ int32_t load_src(const Params& p, int k, int64_t r) {
   return __ldg(p.nbr + (int64_t)(p.flip_k ? p.kvol - 1 - k : k) * p.n_rows + r);
 }
 
-__global__ void __launch_bounds__(kThreads3) gather_gemm_tc3_kernel(
+// union of the active-offset masks of the T row tiles of a CTA tile
+template <int T>
+__device__ __forceinline__ KMask load_mask_t(const Params& p, int ctile) {
+  KMask m = load_mask(p, ctile * T);
+  if (T == 2 && ctile * T + 1 < p.n_tiles128) {
+    const KMask m2 = load_mask(p, ctile * T + 1);
+    m.w0 |= m2.w0;
+    m.w1 |= m2.w1;
+    m.w2 |= m2.w2;
+    m.w3 |= m2.w3;
+  }
+  return m;
+}
+
+template <int T>
+__global__ void __launch_bounds__(128 * T + 192) gather_gemm_tc3_kernel(
     const Params p, const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm32) {
+  constexpr int kProdWarps = 4 * T;
+  constexpr int kRows = kTileM * T;
+  constexpr int kAStage = kABytes * T;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   __shared__ __align__(8) uint64_t s_full[8];
@@ -150,7 +237,7 @@ __global__ void __launch_bounds__(kThreads3) gather_gemm_tc3_kernel(
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(smem_u32(&s_full[s]), kProducerThreads + 1);   // 128 gather threads + TMA expect_tx
+      mbar_init(smem_u32(&s_full[s]), 128 * T + 1);            // gather threads + TMA expect_tx
       mbar_init(smem_u32(&s_empty[s]), 1);                     // one tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
@@ -159,29 +246,35 @@ __global__ void __launch_bounds__(kThreads3) gather_gemm_tc3_kernel(
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) tmem_alloc(smem_u32(&s_tmem), (uint32_t)p.tmem_cols);
+  if (warp == kProdWarps) tmem_alloc(smem_u32(&s_tmem), (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
 
-  if (warp < 4) {
+  if (warp < kProdWarps) {
     // ================================================================ A producers
     Ring ring(S);
+    GatherSlots g;
+    slots_init(g, warp, lane);
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const KMask amask = load_mask(p, tile);
-      const int64_t my_row = (int64_t)tile * kTileM + warp * 32 + lane;
+      const KMask amask = load_mask_t<T>(p, tile);
+      const int64_t my_row = (int64_t)tile * kRows + warp * 32 + lane;
       int k = next_active(amask, -1, p.kvol);
       int32_t nxt = k < p.kvol ? load_src(p, k, my_row) : -1;
       while (k < p.kvol) {
-        const int32_t src = nxt;
+        slots_set_rows(g, p, nxt, lane);
         const int kn = next_active(amask, k, p.kvol);
         if (kn < p.kvol) nxt = load_src(p, kn, my_row);        // prefetch the next offset's map
-        for (int c = 0; c < n_chunks; ++c) {
+        for (int c = 0; c < p.n64; ++c) {
           if (ring.wraps > 0) mbar_wait(smem_u32(&s_empty[ring.s]), (ring.wraps - 1) & 1);
-          const uint32_t a_base = smem_base + ring.s * p.stage_stride;
-          if (c < p.n64) gather_chunk<128>(p, src, a_base, c * 64, warp, lane);
-          else gather_chunk<64>(p, src, a_base, p.n64 * 64, warp, lane);
+          gather_wide(g, smem_base + ring.s * p.stage_stride, c * 64);
+          cp_async_mbar_arrive_noinc(smem_u32(&s_full[ring.s]));
+          ring.advance();
+        }
+        if (p.tail32) {
+          if (ring.wraps > 0) mbar_wait(smem_u32(&s_empty[ring.s]), (ring.wraps - 1) & 1);
+          gather_tail(g, smem_base + ring.s * p.stage_stride);
           cp_async_mbar_arrive_noinc(smem_u32(&s_full[ring.s]));
           ring.advance();
         }
@@ -189,7 +282,7 @@ __global__ void __launch_bounds__(kThreads3) gather_gemm_tc3_kernel(
       }
     }
     cp_async_wait<0>();
-  } else if (warp == 4) {
+  } else if (warp == kProdWarps) {
     // ================================================================= MMA issuer
     if (lane == 0) {
       const int n_half = p.c_res > 256 ? p.c_res / 2 : p.c_res;
@@ -197,38 +290,46 @@ __global__ void __launch_bounds__(kThreads3) gather_gemm_tc3_kernel(
       Ring ring(S);
       int used = 0;                                     // non-empty tiles so far (accumulator turn)
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const KMask amask = load_mask(p, tile);
+        const KMask amask = load_mask_t<T>(p, tile);
         if (!amask.any()) continue;
         const int ab = p.acc_bufs == 2 ? (used & 1) : 0;
         const int turn = p.acc_bufs == 2 ? (used >> 1) : used;   // uses of this accumulator before
         if (turn > 0) mbar_wait(smem_u32(&s_acc_empty[ab]), (turn - 1) & 1);
         tc_fence_after();
-        const uint32_t tmem_acc = tmem_base + (uint32_t)(ab * p.acc_stride);
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(ab * T * p.acc_stride);
         uint32_t acc_flag = 0;
         for (int k = next_active(amask, -1, p.kvol); k < p.kvol; k = next_active(amask, k, p.kvol)) {
           for (int c = 0; c < n_chunks; ++c) {
             mbar_wait(smem_u32(&s_full[ring.s]), ring.wraps & 1);
             tc_fence_after();
             const uint32_t a_base = smem_base + ring.s * p.stage_stride;
-            const uint32_t b_base = a_base + kABytes;
+            const uint32_t b_base = a_base + kAStage;
             if (c < p.n64) {
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
-                const uint64_t ad = make_desc<128>(a_base + kk * 32);
-                umma_f16(tmem_acc, ad, make_desc<128>(b_base + kk * 32), idesc, acc_flag);
-                if (n_half != p.c_res)
-                  umma_f16(tmem_acc + (uint32_t)n_half, ad,
-                           make_desc<128>(b_base + n_half * 128 + kk * 32), idesc, acc_flag);
+                const uint64_t bd = make_desc<128>(b_base + kk * 32);
+#pragma unroll
+                for (int t = 0; t < T; ++t) {                  // one weight tile, T row tiles
+                  const uint64_t ad = make_desc<128>(a_base + t * kABytes + kk * 32);
+                  umma_f16(tmem_acc + (uint32_t)(t * p.acc_stride), ad, bd, idesc, acc_flag);
+                  if (n_half != p.c_res)
+                    umma_f16(tmem_acc + (uint32_t)(t * p.acc_stride + n_half), ad,
+                             make_desc<128>(b_base + n_half * 128 + kk * 32), idesc, acc_flag);
+                }
                 acc_flag = 1;
               }
             } else {
 #pragma unroll
               for (int kk = 0; kk < 2; ++kk) {
-                const uint64_t ad = make_desc<64>(a_base + kk * 32);
-                umma_f16(tmem_acc, ad, make_desc<64>(b_base + kk * 32), idesc, acc_flag);
-                if (n_half != p.c_res)
-                  umma_f16(tmem_acc + (uint32_t)n_half, ad,
-                           make_desc<64>(b_base + n_half * 64 + kk * 32), idesc, acc_flag);
+                const uint64_t bd = make_desc<64>(b_base + kk * 32);
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                  const uint64_t ad = make_desc<64>(a_base + t * kABytes + kk * 32);
+                  umma_f16(tmem_acc + (uint32_t)(t * p.acc_stride), ad, bd, idesc, acc_flag);
+                  if (n_half != p.c_res)
+                    umma_f16(tmem_acc + (uint32_t)(t * p.acc_stride + n_half), ad,
+                             make_desc<64>(b_base + n_half * 64 + kk * 32), idesc, acc_flag);
+                }
                 acc_flag = 1;
               }
             }
@@ -241,18 +342,18 @@ __global__ void __launch_bounds__(kThreads3) gather_gemm_tc3_kernel(
       }
     }
     tc_fence_before();
-  } else if (warp == 5) {
+  } else if (warp == kProdWarps + 1) {
     // ================================================ B producer (TMA weight tiles)
     if (lane == 0) {
       const int n_half = p.c_res > 256 ? p.c_res / 2 : p.c_res;
       Ring ring(S);
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const KMask amask = load_mask(p, tile);
+        const KMask amask = load_mask_t<T>(p, tile);
         for (int k = next_active(amask, -1, p.kvol); k < p.kvol; k = next_active(amask, k, p.kvol)) {
           for (int c = 0; c < n_chunks; ++c) {
             if (ring.wraps > 0) mbar_wait(smem_u32(&s_empty[ring.s]), (ring.wraps - 1) & 1);
             const uint32_t bar = smem_u32(&s_full[ring.s]);
-            const uint32_t b_base = smem_base + ring.s * p.stage_stride + kABytes;
+            const uint32_t b_base = smem_base + ring.s * p.stage_stride + kAStage;
             const bool wide = c < p.n64;
             const int rowb = wide ? 128 : 64;
             mbar_arrive_expect_tx(bar, (uint32_t)(p.c_res * rowb));
@@ -270,16 +371,19 @@ __global__ void __launch_bounds__(kThreads3) gather_gemm_tc3_kernel(
     const int q = warp & 3;                              // TMEM lane quarter this warp may read
     int used = 0;
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const KMask amask = load_mask(p, tile);
+      const KMask amask = load_mask_t<T>(p, tile);
       const bool any = amask.any();
       const int ab = p.acc_bufs == 2 ? (used & 1) : 0;
       const int turn = p.acc_bufs == 2 ? (used >> 1) : used;
       if (any) {
-        mbar_wait(smem_u32(&s_acc_full[ab]), turn & 1);
+        mbar_wait_backoff(smem_u32(&s_acc_full[ab]), turn & 1);   // a whole main loop away: sleep
         tc_fence_after();
       }
-      const int64_t r = (int64_t)tile * kTileM + q * 32 + lane;
-      const uint32_t t_lane = tmem_base + (uint32_t)(ab * p.acc_stride) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int t = 0; t < T; ++t) {
+      const int64_t r = (int64_t)tile * kRows + t * kTileM + q * 32 + lane;
+      const int64_t r_out = (p.row_perm && r < p.n_rows) ? (int64_t)__ldg(p.row_perm + r) : r;
+      const uint32_t t_lane = tmem_base + (uint32_t)((ab * T + t) * p.acc_stride) + ((uint32_t)(q * 32) << 16);
       for (int c0 = 0; c0 < p.c_res; c0 += 16) {
         uint32_t v[16];
         if (any) {
@@ -297,10 +401,11 @@ __global__ void __launch_bounds__(kThreads3) gather_gemm_tc3_kernel(
             if (p.bias) f += __half2float(__ldg(p.bias + c0 + j));
             h[j] = __float2half_rn(f);
           }
-          uint4* dst = reinterpret_cast<uint4*>(p.out + r * p.c_res + c0);
+          uint4* dst = reinterpret_cast<uint4*>(p.out + r_out * p.c_res + c0);
           dst[0] = reinterpret_cast<const uint4*>(h)[0];
           dst[1] = reinterpret_cast<const uint4*>(h)[1];
         }
+      }
       }
       if (any) {
         tc_fence_before();
@@ -312,7 +417,7 @@ __global__ void __launch_bounds__(kThreads3) gather_gemm_tc3_kernel(
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kProdWarps) {
     tc_fence_after();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
@@ -356,17 +461,18 @@ static bool make_weight_map(CUtensorMap* tm, const void* w, int k, int c_res, in
 
 // wt: [K][c_res][c_red] fp16 (K-major B operand); nbr and tile_mask must be non-null
 int launch_gather_gemm_tc3(const void* in, const void* wt, int k, int c_red, int c_res, int flip_k,
-                           const int32_t* nbr, const uint32_t* tile_mask, int64_t n_rows,
-                           const void* bias, void* out, cudaStream_t st) {
+                           const int32_t* nbr, const uint32_t* tile_mask, const int32_t* row_perm,
+                           int64_t n_rows, const void* bias, void* out, cudaStream_t st) {
   using namespace tc3;
   Params p;
   p.in = reinterpret_cast<const __half*>(in);
   p.nbr = nbr;
   p.tile_mask = tile_mask;
+  p.row_perm = row_perm;
   p.bias = reinterpret_cast<const __half*>(bias);
   p.out = reinterpret_cast<__half*>(out);
   p.n_rows = n_rows;
-  p.n_tiles = (int)ceil_div(n_rows, kTileM);
+  p.n_tiles128 = (int)ceil_div(n_rows, kTileM);
   p.kvol = k;
   p.c_red = c_red;
   p.c_res = c_res;
@@ -381,14 +487,25 @@ int launch_gather_gemm_tc3(const void* in, const void* wt, int k, int c_red, int
                          "b2s_conv_gather_gemm: cuTensorMapEncodeTiled failed (64-wide)");
   if (p.tail32) B2S_REQUIRE(make_weight_map(&tm32, wt, k, c_res, c_red, 32, n_half), B2S_ERR_CUDA,
                             "b2s_conv_gather_gemm: cuTensorMapEncodeTiled failed (32-wide)");
-  // accumulator layout in TMEM: power-of-two stride per accumulator, two of them when they fit
+  // accumulator layout in TMEM: power-of-two column stride per accumulator
   int stride = 32;
   while (stride < c_res) stride <<= 1;
   p.acc_stride = stride;
-  p.acc_bufs = 2 * stride <= 512 ? 2 : 1;
-  p.tmem_cols = stride * p.acc_bufs;
+  // T = 2 row tiles per CTA share every weight tile.  Measured (profiles/r1_conv_microbench_v3.txt):
+  // a win only for the narrowest layers (C_res <= 32: 175 -> 122 us); for C_res >= 64 two
+  // independent 128-row CTAs per SM are faster than one 256-row CTA (the shared-memory write +
+  // read volume of the mostly-empty gathered tiles, not the weight stream, is what saturates).
+  int T = stride <= 32 ? 2 : 1;
+  {
+    const char* et = getenv("B2S_TC_T");
+    if (et && (atoi(et) == 1 || atoi(et) == 2) && stride * atoi(et) <= 512) T = atoi(et);
+  }
+  if (p.n_tiles128 < 2 * sm_count()) T = 1;            // small levels: keep every SM busy
+  p.acc_bufs = stride * T * 2 <= 512 ? 2 : 1;
+  p.tmem_cols = stride * T * p.acc_bufs;
+  p.n_tiles = (p.n_tiles128 + T - 1) / T;
   const int rowb_max = p.n64 ? 128 : 64;
-  p.stage_stride = (kABytes + ((c_res + 7) / 8) * 8 * rowb_max + 1023) & ~1023;
+  p.stage_stride = (T * kABytes + ((c_res + 7) / 8) * 8 * rowb_max + 1023) & ~1023;
   // two CTAs per SM when both the ring (>= 3 stages) and the TMEM columns fit twice
   const int budget2 = 111 * 1024, budget1 = 222 * 1024;
   int ctas_per_sm = 1;
@@ -409,17 +526,20 @@ int launch_gather_gemm_tc3(const void* in, const void* wt, int k, int c_red, int
   B2S_REQUIRE(stages >= 2, B2S_ERR_UNSUPPORTED, "b2s_conv_gather_gemm: tile does not fit (C=%d)", c_res);
   p.stages = stages;
   const size_t smem = (size_t)stages * p.stage_stride + 1024;
-  static size_t smem_opt_in = 0;
-  if (smem > smem_opt_in) {
-    cudaError_t e = cudaFuncSetAttribute(gather_gemm_tc3_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t smem_opt_in[3] = {0, 0, 0};
+  if (smem > smem_opt_in[T]) {
+    cudaError_t e = T == 2 ? cudaFuncSetAttribute(gather_gemm_tc3_kernel<2>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(gather_gemm_tc3_kernel<1>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     B2S_REQUIRE(e == cudaSuccess, B2S_ERR_CUDA, "b2s_conv_gather_gemm: cannot opt in to %zu B smem: %s",
                 smem, cudaGetErrorString(e));
-    smem_opt_in = smem;
+    smem_opt_in[T] = smem;
   }
   int grid = sm_count() * ctas_per_sm;
   if (grid > p.n_tiles) grid = p.n_tiles;
-  gather_gemm_tc3_kernel<<<grid, kThreads3, smem, st>>>(p, tm64, tm32);
+  if (T == 2) gather_gemm_tc3_kernel<2><<<grid, 128 * 2 + 192, smem, st>>>(p, tm64, tm32);
+  else gather_gemm_tc3_kernel<1><<<grid, 128 + 192, smem, st>>>(p, tm64, tm32);
   return B2S_OK;
 }
 

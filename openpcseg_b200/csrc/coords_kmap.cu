@@ -191,6 +191,23 @@ __global__ void __launch_bounds__(256) kmap_probe_kernel(
     if (s_cnt[t]) atomicAdd(nbsizes + t, s_cnt[t]);
 }
 
+// one CTA per 128-row tile: bit k <=> some row of the tile has a neighbour for offset k
+__global__ void __launch_bounds__(128) tile_mask_kernel(const int32_t* __restrict__ nbr, int kvol, int64_t n,
+                                                         uint32_t* __restrict__ mask) {
+  __shared__ uint32_t s_m[4];
+  const int words = (kvol + 31) >> 5;
+  if (threadIdx.x < 4) s_m[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  for (int k = 0; k < kvol; ++k) {
+    const bool have = r < n && __ldg(nbr + (int64_t)k * n + r) >= 0;
+    const unsigned b = __ballot_sync(0xffffffffu, have);
+    if ((threadIdx.x & 31) == 0 && b) atomicOr(&s_m[k >> 5], 1u << (k & 31));
+  }
+  __syncthreads();
+  if (threadIdx.x < words) mask[(int64_t)blockIdx.x * words + threadIdx.x] = s_m[threadIdx.x];
+}
+
 struct PairOf {
   const int32_t* nbr;
   int32_t n_out;
@@ -385,6 +402,15 @@ int b2s_kmap_build(const int32_t* in_coords, int64_t n_in, const int32_t* out_co
       t, reinterpret_cast<const int4*>(out_coords), n_out, n_in, offsets, k, nbr_out, nbr_in,
       nbsizes, tile_mask_out, nbr_in ? tile_mask_in : nullptr);
   B2S_CHECK_LAUNCH("b2s_kmap_build");
+  return B2S_OK;
+}
+
+int b2s_tile_mask(const int32_t* nbr, int32_t k, int64_t n, uint32_t* tile_mask, b2s_stream_t stream) {
+  B2S_REQUIRE(k >= 1 && k <= 128 && n >= 0, B2S_ERR_INVALID, "b2s_tile_mask: bad sizes");
+  if (n == 0) return B2S_OK;
+  B2S_REQUIRE(nbr && tile_mask, B2S_ERR_INVALID, "b2s_tile_mask: null pointer");
+  tile_mask_kernel<<<(unsigned)ceil_div(n, 128), 128, 0, as_stream(stream)>>>(nbr, k, n, tile_mask);
+  B2S_CHECK_LAUNCH("b2s_tile_mask");
   return B2S_OK;
 }
 

@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--layers", default=",".join(LAYERS))
     ap.add_argument("--once", action="store_true", help="one launch per kernel (for ncu)")
+    ap.add_argument("--hash-order", action="store_true",
+                    help="put every level in ascending-hash row order (what initial_voxelize produces)")
     a = ap.parse_args()
     dev = torch.device("cuda")
     b = make_batch(list(range(a.batch)))
@@ -38,6 +40,8 @@ def main():
     levels = [coords]
     for lv in range(4):
         levels.append(F.spdownsample(levels[-1], 2, 2, 2 ** lv))
+    if a.hash_order:
+        levels = [c[torch.argsort(F.sphash(c))].contiguous() for c in levels]
     kmaps = {}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     print(f"batch {a.batch}: voxels per level {[int(c.shape[0]) for c in levels]}")
@@ -53,10 +57,11 @@ def main():
         x = torch.randn(n, cin, device=dev, dtype=torch.float16)
         gy = torch.randn(n, cout, device=dev, dtype=torch.float16)
         w = (torch.randn(27, cin, cout, device=dev) / (27 * cin) ** 0.5).half()
-        gmap, flip, gmask = km.in_gather_map()
+        omap, omask, operm = km.out_gather_map()
+        gmap, flip, gmask, gperm = km.in_gather_map()
         runs = {
-            "fwd": lambda: B.conv_gather_gemm(x, w, km.nbr_out, n, False, False, tile_mask=km.mask_out),
-            "dgrad": lambda: B.conv_gather_gemm(gy, w, gmap, n, True, flip, tile_mask=gmask),
+            "fwd": lambda: B.conv_gather_gemm(x, w, omap, n, False, False, tile_mask=omask, row_perm=operm),
+            "dgrad": lambda: B.conv_gather_gemm(gy, w, gmap, n, True, flip, tile_mask=gmask, row_perm=gperm),
             "wgrad": lambda: B.conv_wgrad(x, gy, 27, pairs, km.nbsizes32, False),
         }
         useful = 2.0 * m * cin * cout
