@@ -572,13 +572,16 @@ int launch_wgrad_tc(const void* in, const void* gout, const int32_t* nbmaps,
   if (stages > 6) stages = 6;
   B2S_REQUIRE(stages >= 2, B2S_ERR_UNSUPPORTED, "b2s_conv_wgrad: tile does not fit (C_out=%d)", c_out);
   p.stages = stages;
-  // unit size: enough units to fill the machine ~3x, at least 8 stages per unit
+  // unit size: ~6 units per CTA slot so that the static round-robin stays balanced even though the
+  // per-offset pair counts differ by 10x (the centre offset has N pairs, corner offsets ~N/20);
+  // at least 16 stages per unit so the fp32 reds of the epilogue stay a few % of the gathered bytes.
   // (the true pair count lives on the device; on LiDAR surfaces ~1/4 of the K*N slots exist)
   const int sms = sm_count();
   const int64_t est = k > 1 ? n_pairs_bound / 4 + 1 : n_pairs_bound;
-  int64_t per = est / ((int64_t)sms * 3) + 1;
+  const int64_t slots_est = (int64_t)sms * (two_per_sm ? 2 : 1);
+  int64_t per = est / (slots_est * 5) + 1;
   int64_t unit = ((per + kRows - 1) / kRows) * kRows;
-  if (unit < 8 * kRows) unit = 8 * kRows;
+  if (unit < 16 * kRows) unit = 16 * kRows;
   if (unit > 256 * kRows) unit = 256 * kRows;
   p.unit_pairs = (int)unit;
   const size_t smem = (size_t)stages * stage + 1024;
