@@ -38,9 +38,9 @@ FULL_AZIMUTH = 1875
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("B2S_BENCH_BATCH", 8)),
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("B2S_BENCH_BATCH", 16)),
                     help="scans per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "fp32"])

@@ -170,6 +170,14 @@ int b2s_devoxelize_bwd(int32_t dtype, const void* grad_pts, const int32_t* idx,
                        const float* weights, int64_t n_pts, int64_t n_vox, int32_t c,
                        void* grad_vox, float* acc, b2s_stream_t stream);
 
+/* Scatter-max of point rows into voxel rows (Cylinder3D's torch_scatter.scatter_max,
+ * tools/utils/common/seg_utils.py:172-188, pcseg/model/segmentor/voxel/cylinder3d/
+ * cylinder_ts.py:24-43): out[idx[i], j] = max over i of feats[i, j]; arg int64 [m, c] = the
+ * smallest contributing row (n for empty voxels, whose out is 0) - what backward needs.
+ * keys uint32 [m, c] is scratch.                                                             */
+int b2s_scatter_max(int32_t dtype, const void* feats, const int64_t* idx, int64_t n, int32_t c, int64_t m,
+                    void* out, int64_t* arg, uint32_t* keys, b2s_stream_t stream);
+
 /* Fused voxel_to_point map (pcseg/model/segmentor/voxel/minkunet/utils.py:73-81 +
  * calc_ti_weights, TS/nn/functional/devoxelize.py:10-48): for every point, the 8
  * corner voxel rows (or -1) at `stride` and the fp32 trilinear weights.

@@ -22,3 +22,7 @@ def install_as_torchsparse() -> None:
     from . import backend
     sys.modules["torchsparse.backend"] = backend
     pkg.backend = backend
+    try:                                  # Cylinder3D's scatter_max when torch_scatter is not installed
+        importlib.import_module("torch_scatter")
+    except ImportError:
+        sys.modules["torch_scatter"] = importlib.import_module("openpcseg_b200.torch_scatter")

@@ -45,6 +45,7 @@ _SIGNATURES = {
     "b2s_voxelize_bwd": (c_int32, [c_int32, _P, _P, _P, c_int64, c_int64, c_int32, _P, _P]),
     "b2s_devoxelize_fwd": (c_int32, [c_int32, _P, _P, _P, c_int64, c_int64, c_int32, _P, _P]),
     "b2s_devoxelize_bwd": (c_int32, [c_int32, _P, _P, _P, c_int64, c_int64, c_int32, _P, _P, _P]),
+    "b2s_scatter_max": (c_int32, [c_int32, _P, _P, c_int64, c_int32, c_int64, _P, _P, _P, _P]),
     "b2s_trilinear_map": (c_int32, [_P, c_int64, c_int32, _P, c_int64, _P, _P, _P]),
     "b2s_ti_weights": (c_int32, [_P, c_int64, _P, c_float, _P, _P]),
     "b2s_bn_supported": (c_int32, [c_int32, c_int32]),

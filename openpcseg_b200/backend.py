@@ -362,6 +362,20 @@ def devoxelize_backward(grad_pts: torch.Tensor, idx: torch.Tensor, weights: torc
     return out
 
 
+def scatter_max(feats: torch.Tensor, idx: torch.Tensor, m: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """(out [m, c], arg int64 [m, c]) like torch_scatter.scatter_max(feats, idx, dim=0, dim_size=m)."""
+    _cuda(feats, idx)
+    feats, idx = feats.contiguous(), idx.long().contiguous()
+    n, c = feats.shape
+    out = torch.empty((m, c), dtype=feats.dtype, device=feats.device)
+    arg = torch.empty((m, c), dtype=torch.int64, device=feats.device)
+    keys = torch.empty((m, c), dtype=torch.int32, device=feats.device)
+    check(_lib.lib().b2s_scatter_max(_dtype_code(feats), feats.data_ptr(), idx.data_ptr(), n, c, int(m),
+                                     out.data_ptr(), arg.data_ptr(), keys.data_ptr(), _stream()),
+          "scatter_max", launches=3)
+    return out, arg
+
+
 def trilinear_map(pts: torch.Tensor, vox_coords: torch.Tensor, stride: int,
                   table: Optional[HashTable] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """(idx int32 [N, 8], weights fp32 [N, 8]) of voxel_to_point at ``stride`` (fused)."""

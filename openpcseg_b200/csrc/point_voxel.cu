@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(256) devoxelize_fwd_kernel(const T* __restrict
       int32_t r = __ldg(idx + p * 8 + k);
       if (r < 0) continue;
       float wk = __ldg(w + p * 8 + k);
+      if (wk == 0.f) continue;       // on-grid points: 7 of the 8 trilinear weights are exactly 0
       Vec<T, V> v;
       v.load(feats + (int64_t)r * c + ch);
 #pragma unroll
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(256) devoxelize_bwd_kernel(const T* __restrict
       int32_t r = __ldg(idx + p * 8 + k);
       if (r < 0) continue;
       float wk = __ldg(w + p * 8 + k);
+      if (wk == 0.f) continue;
       float v[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) v[j] = wk * g.get(j);
@@ -316,6 +318,64 @@ __global__ void __launch_bounds__(256) denselize_bwd_kernel(const float* __restr
   }
 }
 
+// ---------------------------------------------------------------- scatter-max (Cylinder3D)
+// out[idx[i], j] = max_i feats[i, j]; arg[idx[i], j] = smallest i attaining it (for backward).
+// Replaces torch_scatter.scatter_max in seg_utils.voxelize / initial_voxelize_max
+// (tools/utils/common/seg_utils.py:172-188, cylinder_ts.py:24-43).  fp32 keys are mapped to
+// order-preserving unsigned ints so one atomicMax per element suffices.
+__device__ __forceinline__ uint32_t float_key(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) scatter_max_key_kernel(const T* __restrict__ feats,
+                                                              const int64_t* __restrict__ idx, int64_t n,
+                                                              int c, int64_t m, uint32_t* __restrict__ keys) {
+  const int64_t total = n * c;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / c;
+    const int j = (int)(t - i * c);
+    const int64_t v = __ldg(idx + i);
+    if (v < 0 || v >= m) continue;
+    atomicMax(keys + v * c + j, float_key(FeatIO<T>::load(feats + t)));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) scatter_max_arg_kernel(const T* __restrict__ feats,
+                                                              const int64_t* __restrict__ idx, int64_t n,
+                                                              int c, int64_t m,
+                                                              const uint32_t* __restrict__ keys,
+                                                              int64_t* __restrict__ arg) {
+  const int64_t total = n * c;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = t / c;
+    const int j = (int)(t - i * c);
+    const int64_t v = __ldg(idx + i);
+    if (v < 0 || v >= m) continue;
+    if (float_key(FeatIO<T>::load(feats + t)) == keys[v * c + j])
+      atomicMin(reinterpret_cast<unsigned long long*>(arg + v * c + j), (unsigned long long)i);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) scatter_max_finish_kernel(const uint32_t* __restrict__ keys,
+                                                                 int64_t* __restrict__ arg, int64_t total,
+                                                                 int64_t n, T* __restrict__ out) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const bool empty = keys[t] == 0u;          // no row mapped here: torch_scatter leaves 0 / arg = n
+    FeatIO<T>::store(out + t, empty ? 0.f : key_float(keys[t]));
+    if (empty) arg[t] = n;
+  }
+}
+
 template <typename T>
 constexpr int vec_width() { return sizeof(T) == 4 ? 4 : 8; }
 
@@ -441,6 +501,35 @@ int b2s_devoxelize_bwd(int32_t dtype, const void* grad_pts, const int32_t* idx,
     f32_to_f16_kernel<<<grid_for(n_vox * c, 256), 256, 0, st>>>(acc, n_vox * c,
                                                                 reinterpret_cast<__half*>(grad_vox));
   B2S_CHECK_LAUNCH("b2s_devoxelize_bwd");
+  return B2S_OK;
+}
+
+int b2s_scatter_max(int32_t dtype, const void* feats, const int64_t* idx, int64_t n, int32_t c, int64_t m,
+                    void* out, int64_t* arg, uint32_t* keys, b2s_stream_t stream) {
+  B2S_REQUIRE(dtype == B2S_F32 || dtype == B2S_F16, B2S_ERR_INVALID, "b2s_scatter_max: dtype");
+  B2S_REQUIRE(n >= 0 && c >= 1 && m >= 0, B2S_ERR_INVALID, "b2s_scatter_max: bad sizes");
+  if (m == 0) return B2S_OK;
+  B2S_REQUIRE(out && arg && keys && (n == 0 || (feats && idx)), B2S_ERR_INVALID,
+              "b2s_scatter_max: null pointer");
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(keys, 0, (size_t)m * c * sizeof(uint32_t), st);      // key 0 < every float key
+  cudaMemsetAsync(arg, 0x7F, (size_t)m * c * sizeof(int64_t), st);     // +inf for atomicMin
+  if (n > 0) {
+    const int g = grid_for(n * c, 256);
+    if (dtype == B2S_F32) {
+      scatter_max_key_kernel<float><<<g, 256, 0, st>>>(reinterpret_cast<const float*>(feats), idx, n, c, m, keys);
+      scatter_max_arg_kernel<float><<<g, 256, 0, st>>>(reinterpret_cast<const float*>(feats), idx, n, c, m, keys, arg);
+    } else {
+      scatter_max_key_kernel<__half><<<g, 256, 0, st>>>(reinterpret_cast<const __half*>(feats), idx, n, c, m, keys);
+      scatter_max_arg_kernel<__half><<<g, 256, 0, st>>>(reinterpret_cast<const __half*>(feats), idx, n, c, m, keys, arg);
+    }
+  }
+  const int g2 = grid_for(m * c, 256);
+  if (dtype == B2S_F32)
+    scatter_max_finish_kernel<float><<<g2, 256, 0, st>>>(keys, arg, m * c, n, reinterpret_cast<float*>(out));
+  else
+    scatter_max_finish_kernel<__half><<<g2, 256, 0, st>>>(keys, arg, m * c, n, reinterpret_cast<__half*>(out));
+  B2S_CHECK_LAUNCH("b2s_scatter_max");
   return B2S_OK;
 }
 

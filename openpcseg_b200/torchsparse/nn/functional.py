@@ -212,6 +212,23 @@ def build_kernel_map(in_coords: torch.Tensor, out_coords: torch.Tensor, kernel_s
 
 
 # ---------------------------------------------------------------------- convolution
+def _cast_weight(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """fp32 master weight -> feature dtype, cached ON the parameter object until it is next updated
+    in place (the reference re-casts on every call through custom_fwd, TS/nn/functional/conv.py:19)."""
+    if weight.dtype == dtype:
+        return weight
+    hit = getattr(weight, "_b2s_cast", None)
+    if hit is not None and hit[0] == weight._version and hit[1] is dtype and hit[2].device == weight.device \
+            and hit[2].shape == weight.shape:
+        return hit[2]
+    w = weight.detach().to(dtype)
+    try:
+        weight._b2s_cast = (weight._version, dtype, w)
+    except AttributeError:
+        pass
+    return w
+
+
 class ConvolutionFunction(Function):
     """out = sum_k gather(in, map_k) @ W[k]  (TS/nn/functional/conv.py:16-119).
 
@@ -222,7 +239,7 @@ class ConvolutionFunction(Function):
     @staticmethod
     def forward(ctx, feats, weight, kmap: KernelMap, transposed: bool):
         feats = feats.contiguous()
-        w = weight.to(feats.dtype)
+        w = _cast_weight(weight, feats.dtype)
         hint = kmap.total_hint()
         if not transposed:
             gmap, mask, perm = kmap.out_gather_map()
@@ -242,7 +259,7 @@ class ConvolutionFunction(Function):
         feats, weight = ctx.saved_tensors
         kmap, transposed = ctx.kmap, ctx.transposed
         grad_out = grad_out.contiguous()
-        w = weight.to(feats.dtype)
+        w = _cast_weight(weight, feats.dtype)
         grad_in = grad_w = None
         hint = kmap.total_hint()
         if ctx.needs_input_grad[0]:
@@ -269,7 +286,7 @@ class _DenseConv(Function):
     def forward(ctx, feats, weight):
         feats = feats.contiguous()
         ctx.save_for_backward(feats, weight)
-        return B.conv_gather_gemm(feats, weight.to(feats.dtype), None, feats.shape[0], False, False)
+        return B.conv_gather_gemm(feats, _cast_weight(weight, feats.dtype), None, feats.shape[0], False, False)
 
     @staticmethod
     @once_differentiable
@@ -278,8 +295,8 @@ class _DenseConv(Function):
         grad_out = grad_out.contiguous()
         grad_in = grad_w = None
         if ctx.needs_input_grad[0]:
-            grad_in = B.conv_gather_gemm(grad_out, weight.to(feats.dtype), None, feats.shape[0], True,
-                                         False)
+            grad_in = B.conv_gather_gemm(grad_out, _cast_weight(weight, feats.dtype), None, feats.shape[0],
+                                         True, False)
         if ctx.needs_input_grad[1]:
             grad_w = B.conv_wgrad(feats, grad_out, 1, None, None, False)[0].to(weight.dtype)
         return grad_in, grad_w

@@ -474,3 +474,30 @@ def test_fused_batch_norm_act(ts, dtype, c, relu, with_res):
     # eval mode falls back to the stock module
     bn_a.eval()
     assert F.batch_norm_act(x, bn_a, relu=relu).shape == x.shape
+
+
+# ------------------------------------------------------------------- scatter-max (a18)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_scatter_max_matches_torch(dtype):
+    from openpcseg_b200.torch_scatter import scatter_max
+    torch.manual_seed(0)
+    n, c, m = 6000, 24, 500
+    src = torch.randn(n, c, device="cuda").to(dtype)
+    src[::50] = -3.0                                       # negative maxima and ties
+    index = torch.randint(0, m - 7, (n,), device="cuda")   # the last 7 voxels stay empty
+    a = src.clone().requires_grad_(True)
+    out, arg = scatter_max(a, index, dim=0, dim_size=m)
+    ref = torch.full((m, c), float("-inf"), device="cuda", dtype=torch.float32)
+    ref.scatter_reduce_(0, index[:, None].expand(-1, c), src.float(), "amax", include_self=True)
+    filled = torch.isfinite(ref)
+    assert torch.equal(out.float()[filled], ref[filled]) and bool((out[~filled] == 0).all())
+    assert bool((arg[~filled] == n).all())
+    # arg points at a row of the right voxel holding the maximum (the smallest such row)
+    rows = arg[filled]
+    cols = torch.arange(c, device="cuda").expand(m, c)[filled]
+    assert torch.equal(src[rows, cols].float(), ref[filled])
+    g = torch.randn(m, c, device="cuda").to(dtype)
+    out.backward(g)
+    exp = torch.zeros(n + 1, c, device="cuda", dtype=dtype)
+    exp.scatter_(0, arg, g)
+    assert torch.equal(a.grad, exp[:n])
