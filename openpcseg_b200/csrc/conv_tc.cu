@@ -373,6 +373,7 @@ struct WParams {
   int64_t n_identity;
   int kvol, c_in, c_out, swap_pairs;
   int m_tiles, unit_pairs, stages, tmem_cols;
+  int dbg;                // ablation: bit0 no gathers, bit1 no MMAs, bit2 no epilogue reds
 };
 
 __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p) {
@@ -456,6 +457,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p) {
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
+          if (p.dbg & 1) break;
           const int rl = g * 4 + sub;                               // row within the warp's 16
           const int row = warp * 16 + rl;
           const int32_t i = __shfl_sync(0xffffffffu, my_i, rl);
@@ -493,7 +495,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p) {
         uint32_t v[16];
         tmem_ld16(t_lane + (uint32_t)c0, v);
         tmem_ld_wait();
-        if (ci < p.c_in) {
+        if (ci < p.c_in && !(p.dbg & 4)) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4)
             red_add_v4(dst + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]),
@@ -513,6 +515,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p) {
           const uint32_t b_base = a_base + a_bytes;
 #pragma unroll
           for (int kk = 0; kk < kRows / 16; ++kk) {
+            if (p.dbg & 2) break;
             const uint64_t ad = make_desc_mn(a_base + kk * 2048, kPanelBytes);
             const uint64_t bd = make_desc_mn(b_base + kk * 2048, kPanelBytes);
             umma_f16(tmem_acc, ad, bd, idesc, (st | kk) ? 1u : 0u);
@@ -564,6 +567,11 @@ int launch_wgrad_tc(const void* in, const void* gout, const int32_t* nbmaps,
   p.c_out = c_out;
   p.swap_pairs = swap_pairs;
   p.m_tiles = (c_in + 127) / 128;
+  p.dbg = 0;
+  {
+    const char* ed = getenv("B2S_WG_DBG");
+    if (ed) p.dbg = atoi(ed);
+  }
   p.tmem_cols = tc::tmem_cols_for(c_out);
   const int stage = (2 + (c_out + 63) / 64) * kPanelBytes;
   int stages = (int)((110 * 1024) / stage);          // two CTAs per SM when >= 3 stages fit twice

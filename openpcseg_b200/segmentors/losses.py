@@ -13,6 +13,20 @@ import torch.nn.functional as TF
 __all__ = ["SegLoss", "lovasz_softmax_flat"]
 
 
+def _cumsum_long_rows(x: torch.Tensor, block: int = 2048) -> torch.Tensor:
+    """Inclusive cumsum along dim 1 of a [C, P] tensor with few, very long rows.  torch.cumsum runs
+    one thread block per row there (1.3 ms for [20, 760k] on B200 = 4.6 % of the training step); a
+    two-level scan (inside 2048-element blocks, then over the block totals) keeps the GPU busy."""
+    c, p = x.shape
+    if p <= 4 * block:
+        return x.cumsum(1)
+    pad = (-p) % block
+    xp = torch.nn.functional.pad(x, (0, pad)).view(c, -1, block)
+    inner = xp.cumsum(2)
+    offsets = inner[:, :, -1].cumsum(1) - inner[:, :, -1]
+    return (inner + offsets[:, :, None]).view(c, -1)[:, :p]
+
+
 def lovasz_softmax_flat(probs: torch.Tensor, labels: torch.Tensor, ignore_index: int) -> torch.Tensor:
     """probs [P, C], labels [P].  Works class-major ([C, P], scans along the contiguous axis:
     torch's outer-dimension cumsum is ~50x slower on a [190k, 20] tensor)."""
@@ -25,8 +39,8 @@ def lovasz_softmax_flat(probs: torch.Tensor, labels: torch.Tensor, ignore_index:
     fg_sorted = torch.gather(fg, 1, perm)
     bg_sorted = torch.gather((1.0 - fg) * valid, 1, perm)
     gts = fg_sorted.sum(1, keepdim=True)
-    inter = gts - fg_sorted.cumsum(1)
-    union = gts + bg_sorted.cumsum(1)
+    inter = gts - _cumsum_long_rows(fg_sorted)
+    union = gts + _cumsum_long_rows(bg_sorted)
     jaccard = 1.0 - inter / union.clamp_min(1e-12)
     grad = torch.cat([jaccard[:, :1], jaccard[:, 1:] - jaccard[:, :-1]], 1)
     per_class = (errors_sorted * grad).sum(1)

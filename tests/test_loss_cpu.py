@@ -7,8 +7,8 @@ from openpcseg_b200.segmentors.losses import SegLoss
 
 def test_segloss_matches_reference_style_loop():
     torch.manual_seed(0)
-    logits = torch.randn(4000, 20, requires_grad=True)
-    target = torch.randint(0, 20, (4000,))
+    logits = torch.randn(20000, 20, requires_grad=True)
+    target = torch.randint(0, 20, (20000,))
     target[target == 7] = 3                                   # one absent class
     mine = SegLoss(ignore_index=0, label_smoothing=0.1)(logits, target)
     ref_net = CpuMinkUNet({})
