@@ -501,3 +501,91 @@ def test_scatter_max_matches_torch(dtype):
     exp = torch.zeros(n + 1, c, device="cuda", dtype=dtype)
     exp.scatter_(0, arg, g)
     assert torch.equal(a.grad, exp[:n])
+
+
+# ------------------------------------ config-4 / config-3 style chains (parity-test cases)
+def test_cylinder_style_chain_fp32(ts):
+    """Cylinder3D's conv vocabulary in one chain: asymmetric (1,3,3) and (3,1,3) submanifold convs,
+    a k3 pooling conv with stride (2,2,1) (slow-path downsample, more outputs than a snap would give)
+    and its transposed conv back (cylinder_ts.py:204-214, 292-301), forward and backward vs the oracle."""
+    F = ts.nn.functional
+    c = multi_batch_cloud(41, n=1500, extent=28, batches=2)
+    rng = np.random.default_rng(41)
+    ci, cm = 8, 16
+    x = rng.standard_normal((len(c), ci)).astype(np.float32)
+    w1 = (rng.standard_normal((9, ci, cm)) / 9).astype(np.float32)
+    w2 = (rng.standard_normal((9, cm, cm)) / 12).astype(np.float32)
+    wp = (rng.standard_normal((27, cm, cm)) / 20).astype(np.float32)
+    wt = (rng.standard_normal((27, cm, ci)) / 20).astype(np.float32)
+    nb1, ns1 = R.build_kmap(c, c, (1, 3, 3))
+    nb2, ns2 = R.build_kmap(c, c, (3, 1, 3))
+    oc = R.spdownsample(c, (2, 2, 1), 3, 1)
+    nbp, nsp = R.build_kmap(c, oc, 3)
+    n, m = len(c), len(oc)
+    y1 = R.conv_forward(x, w1, nb1, ns1, (n, n))
+    y2 = R.conv_forward(y1, w2, nb2, ns2, (n, n))
+    y3 = R.conv_forward(y2, wp, nbp, nsp, (n, m))
+    y4 = R.conv_forward(y3, wt, nbp, nsp, (n, m), transposed=True)
+    go = rng.standard_normal(y4.shape).astype(np.float32)
+    g3, gwt = R.conv_backward(y3, wt, go, nbp, nsp, transposed=True)
+    g2, gwp = R.conv_backward(y2, wp, g3, nbp, nsp)
+    g1, gw2 = R.conv_backward(y1, w2, g2, nb2, ns2)
+    g0, gw1 = R.conv_backward(x, w1, g1, nb1, ns1)
+    xt = dev(x).requires_grad_(True)
+    ws = [dev(a).requires_grad_(True) for a in (w1, w2, wp, wt)]
+    s0 = _sparse(ts, xt, dev(c))
+    s1 = F.conv3d(s0, ws[0], (1, 3, 3))
+    s2 = F.conv3d(s1, ws[1], (3, 1, 3))
+    s3 = F.conv3d(s2, ws[2], 3, stride=(2, 2, 1))
+    s4 = F.conv3d(s3, ws[3], 3, stride=(2, 2, 1), transposed=True)
+    assert eq(s3.coords, oc) and s3.stride == (2, 2, 1) and eq(s4.coords, c)
+    assert rel_err(s3.feats, y3) < FP32_TOL and rel_err(s4.feats, y4) < FP32_TOL
+    s4.feats.backward(dev(go))
+    assert rel_err(xt.grad, g0) < 2 * FP32_TOL
+    for got, exp in zip(ws, (gw1, gw2, gwp, gwt)):
+        assert rel_err(got.grad, exp) < 2 * FP32_TOL
+
+
+def test_spvcnn_style_point_voxel_fusion(ts):
+    """SPVCNN's extra hot-path calls: point_to_voxel (scatter-mean of point features onto a strided
+    level) feeding a conv, and voxel_to_point of the result, summed with a point branch
+    (spvcnn.py:411-433), forward + backward vs the oracle."""
+    from openpcseg_b200.segmentors import initial_voxelize, point_to_voxel, voxel_to_point
+    F = ts.nn.functional
+    rng = np.random.default_rng(5)
+    n, cpt = 4000, 16
+    pts = np.concatenate([rng.uniform(0, 30, (n, 3)), rng.integers(0, 2, (n, 1))], 1).astype(np.float32)
+    pf = rng.standard_normal((n, cpt)).astype(np.float32)
+    wd = (rng.standard_normal((8, cpt, cpt)) / 8).astype(np.float32)
+    wc = (rng.standard_normal((27, cpt, cpt)) / 20).astype(np.float32)
+    # oracle
+    vc, vf, idx, cnt, nfc = R.initial_voxelize(pts, pf, 1.0, 1.0)
+    oc = R.spdownsample(vc, 2, 2, 1)
+    nbd, nsd = R.build_kmap(vc, oc, 2)
+    x1 = R.conv_forward(vf, wd, nbd, nsd, (len(vc), len(oc)))
+    pi, pc = R.point_to_voxel_map(nfc, oc, 2)
+    fused = x1 + R.spvoxelize_forward(pf, pi, pc)
+    nbc, nsc = R.build_kmap(oc, oc, 3, 2)
+    x2 = R.conv_forward(fused, wc, nbc, nsc, (len(oc), len(oc)))
+    i8, w8 = R.trilinear_map(nfc, oc, 2)
+    out = R.spdevoxelize_forward(x2, i8, w8) + pf
+    # CUDA path
+    pft = dev(pf).requires_grad_(True)
+    z = ts.PointTensor(pft, dev(pts))
+    v0 = initial_voxelize(z, 1.0, 1.0)
+    assert eq(v0.C, vc)
+    v1 = F.conv3d(v0, dev(wd), 2, stride=2)
+    zf = ts.PointTensor(pft, z.C, idx_query=z.idx_query, weights=z.weights)
+    zf.additional_features = z.additional_features
+    v1 = v1 + point_to_voxel(v1, zf)
+    v2 = F.conv3d(v1, dev(wc), 3)
+    res = voxel_to_point(v2, zf).F + pft
+    assert rel_err(res, out) < 2 * FP32_TOL
+    res.square().sum().backward()
+    # d/d(point feats) through voxelize (twice), both convs and devoxelize, against the oracle chain
+    g = 2 * out
+    gx2 = R.spdevoxelize_backward(g, i8, w8, len(oc))
+    gfused, _ = R.conv_backward(fused, wc, gx2, nbc, nsc)
+    gvf, _ = R.conv_backward(vf, wd, gfused, nbd, nsd)
+    gp = g + R.spvoxelize_backward(gfused, pi, pc, n) + R.spvoxelize_backward(gvf, idx, cnt, n)
+    assert rel_err(pft.grad, gp) < 5 * FP32_TOL
