@@ -119,6 +119,11 @@ int b2s_kmap_pairs(const int32_t* nbr_out, int32_t k, int64_t n_out, int32_t* nb
 /* active-offset masks of the 128-row tiles of an arbitrary gather map nbr [K, n] (e.g. a
  * column-permuted copy of nbr_out): tile_mask uint32 [ceil(n/128)][ceil(K/32)].           */
 int b2s_tile_mask(const int32_t* nbr, int32_t k, int64_t n, uint32_t* tile_mask, b2s_stream_t stream);
+/* int64 sort key per row of a submanifold map (k <= 27): neighbourhood bit pattern, rarest offset
+ * most significant, then a coarse (z, x, y) code of coords >> coord_shift.  Sorting rows by it and
+ * passing the order as row_perm groups rows with equal patterns into the same 128-row tiles.      */
+int b2s_tile_order_key(const int32_t* nbr, int32_t k, int64_t n, const int32_t* nbsizes,
+                       const int32_t* coords, int32_t coord_shift, int64_t* keys, b2s_stream_t stream);
 
 /* ------------------------------------------------------------ convolution ---
  * replaces convolution_forward_cuda / convolution_backward_cuda

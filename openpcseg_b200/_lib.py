@@ -39,6 +39,7 @@ _SIGNATURES = {
     "b2s_conv_gather_gemm": (c_int32, [c_int32, _P, c_int64, _P, c_int32, c_int32, c_int32, c_int32,
                                        c_int32, _P, _P, _P, c_int64, _P, _P, _P, c_size_t, _P]),
     "b2s_tile_mask": (c_int32, [_P, c_int32, c_int64, _P, _P]),
+    "b2s_tile_order_key": (c_int32, [_P, c_int32, c_int64, _P, _P, c_int32, _P, _P]),
     "b2s_conv_wgrad": (c_int32, [c_int32, _P, c_int64, _P, c_int64, c_int32, c_int32, c_int32, _P, _P,
                                  c_int32, _P, _P, c_size_t, _P]),
     "b2s_voxelize_fwd": (c_int32, [c_int32, _P, _P, _P, c_int64, c_int64, c_int32, _P, _P, _P]),

@@ -238,6 +238,16 @@ def tile_mask(nbr: torch.Tensor) -> torch.Tensor:
     return mask
 
 
+def tile_order_key(nbr: torch.Tensor, nbsizes: torch.Tensor, coords: torch.Tensor, coord_shift: int) -> torch.Tensor:
+    """int64 [n] sort keys grouping rows by neighbourhood pattern (b2s_tile_order_key)."""
+    _cuda(nbr, nbsizes, coords)
+    k, n = nbr.shape
+    keys = torch.empty(n, dtype=torch.int64, device=nbr.device)
+    check(_lib.lib().b2s_tile_order_key(nbr.data_ptr(), k, n, nbsizes.data_ptr(), coords.contiguous().data_ptr(),
+                                        int(coord_shift), keys.data_ptr(), _stream()), "tile_order_key")
+    return keys
+
+
 def kmap_pairs(nbr_out: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """(pairs int32 [K*N_out, 2] padded buffer, d_total int64 [1]) - reference pair order."""
     _cuda(nbr_out)

@@ -208,6 +208,38 @@ __global__ void __launch_bounds__(128) tile_mask_kernel(const int32_t* __restric
   if (threadIdx.x < words) mask[(int64_t)blockIdx.x * words + threadIdx.x] = s_m[threadIdx.x];
 }
 
+// Sort key that groups rows with the same neighbourhood pattern: the K presence bits of a row,
+// rarest offset most significant (so rows that need a rare offset cluster into few tiles and all
+// other tiles can skip it), followed by a coarse (z, x, y) code that keeps equal-pattern rows
+// spatially close.  Measured on the synthetic scan (active (tile, offset) fraction): API/hash order
+// 1.00, (z,x,y) order 0.61, this key 0.31 at stride 1; 0.54 -> 0.27 at stride 2.
+__global__ void __launch_bounds__(256) tile_order_key_kernel(const int32_t* __restrict__ nbr, int kvol,
+                                                              int64_t n, const int32_t* __restrict__ nbsizes,
+                                                              const int4* __restrict__ coords, int shift,
+                                                              int64_t* __restrict__ keys) {
+  __shared__ int s_bit[32];
+  if (threadIdx.x < kvol) {
+    const int mine = nbsizes[threadIdx.x];
+    int rank = 0;                                  // 0 = rarest offset
+    for (int j = 0; j < kvol; ++j) {
+      const int o = nbsizes[j];
+      rank += (o < mine || (o == mine && j < (int)threadIdx.x)) ? 1 : 0;
+    }
+    s_bit[threadIdx.x] = kvol - 1 - rank;          // rarest -> most significant of the K bits
+  }
+  __syncthreads();
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n;
+       r += (int64_t)gridDim.x * blockDim.x) {
+    uint64_t m = 0;
+    for (int k = 0; k < kvol; ++k)
+      if (__ldg(nbr + (int64_t)k * n + r) >= 0) m |= 1ULL << s_bit[k];
+    const int4 c = __ldg(coords + r);
+    const uint64_t zc = (uint64_t)((c.z >> shift) & 0x3FF), xc = (uint64_t)((c.x >> shift) & 0x1FFF),
+                   yc = (uint64_t)((c.y >> shift) & 0x1FFF);
+    keys[r] = (int64_t)((m << 36) | (zc << 26) | (xc << 13) | yc);
+  }
+}
+
 struct PairOf {
   const int32_t* nbr;
   int32_t n_out;
@@ -402,6 +434,18 @@ int b2s_kmap_build(const int32_t* in_coords, int64_t n_in, const int32_t* out_co
       t, reinterpret_cast<const int4*>(out_coords), n_out, n_in, offsets, k, nbr_out, nbr_in,
       nbsizes, tile_mask_out, nbr_in ? tile_mask_in : nullptr);
   B2S_CHECK_LAUNCH("b2s_kmap_build");
+  return B2S_OK;
+}
+
+int b2s_tile_order_key(const int32_t* nbr, int32_t k, int64_t n, const int32_t* nbsizes,
+                       const int32_t* coords, int32_t coord_shift, int64_t* keys, b2s_stream_t stream) {
+  B2S_REQUIRE(k >= 1 && k <= 27 && n >= 0 && coord_shift >= 0 && coord_shift < 16, B2S_ERR_INVALID,
+              "b2s_tile_order_key: bad sizes (kernel volume must be <= 27)");
+  if (n == 0) return B2S_OK;
+  B2S_REQUIRE(nbr && nbsizes && coords && keys, B2S_ERR_INVALID, "b2s_tile_order_key: null pointer");
+  tile_order_key_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+      nbr, k, n, nbsizes, reinterpret_cast<const int4*>(coords), coord_shift, keys);
+  B2S_CHECK_LAUNCH("b2s_tile_order_key");
   return B2S_OK;
 }
 

@@ -174,7 +174,7 @@ class KernelMap:
         return 3
 
 
-_TILE_ORDER = os.environ.get("B2S_TILE_ORDER", "zxy")
+_TILE_ORDER = os.environ.get("B2S_TILE_ORDER", "mask")      # "mask" | "zxy" | "none"
 
 
 def _tile_order(coords: torch.Tensor) -> torch.Tensor:
@@ -203,8 +203,15 @@ def build_kernel_map(in_coords: torch.Tensor, out_coords: torch.Tensor, kernel_s
                                                                want_nbr_in=not symmetric)
     km = KernelMap(nbr_out, nbr_in, nbsizes, (in_coords.shape[0], out_coords.shape[0]), symmetric,
                    mask_out, mask_in)
-    if symmetric and _TILE_ORDER == "zxy" and out_coords.shape[0] > 256:
-        perm = _tile_order(out_coords)
+    if symmetric and _TILE_ORDER in ("zxy", "mask") and out_coords.shape[0] > 256:
+        if _TILE_ORDER == "mask" and offsets.shape[0] <= 27:
+            # rows with the same neighbourhood pattern share tiles (rarest offsets first), see
+            # b2s_tile_order_key: halves the active (tile, offset) steps again vs the (z,x,y) order
+            shift = max(int(in_stride[0]).bit_length() - 1, 0) if not isinstance(in_stride, int) \
+                else max(int(in_stride).bit_length() - 1, 0)
+            perm = torch.argsort(B.tile_order_key(nbr_out, nbsizes, out_coords, shift)).int()
+        else:
+            perm = _tile_order(out_coords)
         km.tile_perm = perm
         km.tile_nbr = nbr_out.index_select(1, perm.long()).contiguous()
         km.tile_mask = B.tile_mask(km.tile_nbr)
