@@ -436,53 +436,68 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p) {
       // ---------------------------------------------------------------- producers
       const int sub = lane >> 3, chunk = lane & 7;
       const int2* pr = reinterpret_cast<const int2*>(p.pairs);
-      const int64_t base_q = s_start[k] + lo + warp * 16 + lane;
-      for (int st = 0; st < n_stage; ++st) {
-        if (rwraps > 0) mbar_wait(smem_u32(&s_empty[rs]), (rwraps - 1) & 1);
-        const uint32_t a_base = smem_base + rs * stage_stride;
-        const uint32_t b_base = a_base + a_bytes;
-        // this warp stages rows [warp*16, warp*16+16) of the 64-pair stage
-        int32_t my_i = -1, my_o = -1;
-        if (lane < 16) {
-          const int64_t q = lo + (int64_t)st * kRows + warp * 16 + lane;
-          if (q < hi) {
-            if (pr) {
-              int2 v = __ldg(pr + base_q + (int64_t)st * kRows);
-              my_i = p.swap_pairs ? v.y : v.x;
-              my_o = p.swap_pairs ? v.x : v.y;
-            } else {
-              my_i = my_o = (int32_t)q;
+      const int64_t pair0 = s_start[k];
+      // Pair indices are fetched two stages per load (lanes 0-15: stage st2, lanes 16-31: stage
+      // st2+1; this warp stages rows [warp*16, warp*16+16) of every 64-pair stage) and two such
+      // loads ahead of the gathers that consume them, so the index latency is off the issue path.
+      auto load_idx = [&](int st2, int32_t& ii, int32_t& oo) {
+        ii = -1;
+        oo = -1;
+        const int st = st2 + (lane >> 4);
+        const int64_t q = lo + (int64_t)st * kRows + warp * 16 + (lane & 15);
+        if (st < n_stage && q < hi) {
+          if (pr) {
+            const int2 v = __ldg(pr + pair0 + q);
+            ii = p.swap_pairs ? v.y : v.x;
+            oo = p.swap_pairs ? v.x : v.y;
+          } else {
+            ii = oo = (int32_t)q;
+          }
+        }
+      };
+      int32_t i0, o0, i1, o1, i2, o2;
+      load_idx(0, i0, o0);
+      load_idx(2, i1, o1);
+      for (int st2 = 0; st2 < n_stage; st2 += 2) {
+        load_idx(st2 + 4, i2, o2);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (st2 + h >= n_stage) break;
+          if (rwraps > 0) mbar_wait(smem_u32(&s_empty[rs]), (rwraps - 1) & 1);
+          const uint32_t a_base = smem_base + rs * stage_stride;
+          const uint32_t b_base = a_base + a_bytes;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (p.dbg & 1) break;
+            const int rl = g * 4 + sub;                             // row within the warp's 16
+            const int row = warp * 16 + rl;
+            const int32_t i = __shfl_sync(0xffffffffu, i0, h * 16 + rl);
+            const int32_t o = __shfl_sync(0xffffffffu, o0, h * 16 + rl);
+            const uint32_t off = swz<128>(row, chunk);
+            // A: two 64-channel panels of X
+#pragma unroll
+            for (int pn = 0; pn < 2; ++pn) {
+              const int ch = ch_base + pn * 64 + chunk * 8;
+              if (ch < p.c_in)
+                cp_async16(a_base + pn * kPanelBytes + off,
+                           i >= 0 ? p.x + (int64_t)i * p.c_in + ch : p.x, i >= 0 ? 16u : 0u);
+            }
+            // B: all panels of dY
+            for (int pn = 0; pn < b_panels; ++pn) {
+              const int ch = pn * 64 + chunk * 8;
+              if (ch < p.c_out)
+                cp_async16(b_base + pn * kPanelBytes + off,
+                           o >= 0 ? p.gy + (int64_t)o * p.c_out + ch : p.gy, o >= 0 ? 16u : 0u);
             }
           }
+          // the copy engine signals the stage when this thread's gathers have landed
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(
+                           smem_u32(&s_full[rs]))
+                       : "memory");
+          if (++rs == S) { rs = 0; ++rwraps; }
         }
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (p.dbg & 1) break;
-          const int rl = g * 4 + sub;                               // row within the warp's 16
-          const int row = warp * 16 + rl;
-          const int32_t i = __shfl_sync(0xffffffffu, my_i, rl);
-          const int32_t o = __shfl_sync(0xffffffffu, my_o, rl);
-          const uint32_t off = swz<128>(row, chunk);
-          // A: two 64-channel panels of X
-#pragma unroll
-          for (int pn = 0; pn < 2; ++pn) {
-            const int ch = ch_base + pn * 64 + chunk * 8;
-            if (ch < p.c_in)
-              cp_async16(a_base + pn * kPanelBytes + off, i >= 0 ? p.x + (int64_t)i * p.c_in + ch : p.x,
-                         i >= 0 ? 16u : 0u);
-          }
-          // B: all panels of dY
-          for (int pn = 0; pn < b_panels; ++pn) {
-            const int ch = pn * 64 + chunk * 8;
-            if (ch < p.c_out)
-              cp_async16(b_base + pn * kPanelBytes + off,
-                         o >= 0 ? p.gy + (int64_t)o * p.c_out + ch : p.gy, o >= 0 ? 16u : 0u);
-          }
-        }
-        // the copy engine signals the stage when this thread's gathers have landed
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&s_full[rs]))
-                     : "memory");
-        if (++rs == S) { rs = 0; ++rwraps; }
+        i0 = i1; o0 = o1;
+        i1 = i2; o1 = o2;
       }
 
       // ----------------------------------------------------------------- epilogue
