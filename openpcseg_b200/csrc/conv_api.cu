@@ -16,7 +16,7 @@ int launch_wgrad_simt(const void* in, const void* gout, const int32_t* nbmaps,
 
 // conv_tc.cu
 bool tc_gather_gemm_supported(int c_red, int c_res);
-int launch_gather_gemm_tc(const void* in, const void* weight, int k, int c_in, int c_out,
+int launch_gather_gemm_tc(const void* in, int64_t n_src, const void* weight, int k, int c_in, int c_out,
                           int transpose_w, int flip_k, const int32_t* nbr, const uint32_t* tile_mask,
                           const int32_t* row_perm, int64_t n_rows, const void* bias, void* out, void* ws,
                           size_t ws_bytes, cudaStream_t st);
@@ -69,7 +69,7 @@ int b2s_conv_gather_gemm(int32_t dtype, const void* in, int64_t n_src, const voi
   const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(weight) |
                          reinterpret_cast<uintptr_t>(out)) & 15) == 0;
   if (dtype == B2S_F16 && !force_simt() && aligned && tc_gather_gemm_supported(c_red, c_res)) {
-    int rc = launch_gather_gemm_tc(in, weight, k, c_in, c_out, transpose_w, flip_k, nbr, tile_mask,
+    int rc = launch_gather_gemm_tc(in, n_src, weight, k, c_in, c_out, transpose_w, flip_k, nbr, tile_mask,
                                    row_perm, n_rows, bias, out, ws, ws_bytes, st);
     if (rc != B2S_OK) return rc;
   } else if (dtype == B2S_F16) {

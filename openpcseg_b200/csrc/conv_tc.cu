@@ -270,7 +270,7 @@ size_t tc_gather_gemm_workspace(int k, int c_in, int c_out) {
   return align_up((size_t)k * c_in * c_out * sizeof(__half), 256);   // W^T for the forward pass
 }
 
-int launch_gather_gemm_tc(const void* in, const void* weight, int k, int c_in, int c_out,
+int launch_gather_gemm_tc(const void* in, int64_t n_src, const void* weight, int k, int c_in, int c_out,
                           int transpose_w, int flip_k, const int32_t* nbr, const uint32_t* tile_mask,
                           const int32_t* row_perm, int64_t n_rows, const void* bias, void* out, void* ws,
                           size_t ws_bytes, cudaStream_t st) {
@@ -286,7 +286,9 @@ int launch_gather_gemm_tc(const void* in, const void* weight, int k, int c_in, i
     transpose_weight_kernel<<<g, 256, 0, st>>>(wt, reinterpret_cast<__half*>(ws), c_in, c_out);
     wt = reinterpret_cast<const __half*>(ws);
   }  // input gradient: B_k[n = c_in][c = c_out] = W[k][n][c] is the stored layout already
-  if (!use_v1() && !use_v2() && nbr && tile_mask)      // persistent kernel (needs the tile masks)
+  // persistent kernel: needs the tile masks, and addresses source rows by 32-bit byte offsets
+  const bool small_src = n_src * (int64_t)c_red * 2 < (int64_t)0xFFFFFF00LL;
+  if (!use_v1() && !use_v2() && nbr && tile_mask && small_src)
     return launch_gather_gemm_tc3(in, wt, k, c_red, c_res, flip_k, nbr, tile_mask, row_perm, n_rows, bias,
                                   out, st);
   if (!use_v1())

@@ -81,6 +81,7 @@ struct Params {
   int stages, stage_stride;   // ring of (A tile, weight tile) pairs
   int acc_stride, acc_bufs;   // TMEM columns per accumulator, 1 or 2 accumulators
   int tmem_cols;
+  int dbg;                    // ablation (B2S_TC3_DBG): 1 no gathers, 2 no weight TMA, 4 no MMAs, 8 no stores, 16 no map loads
 };
 
 struct Ring {
@@ -146,14 +147,18 @@ __device__ __forceinline__ KMask load_mask(const Params& p, int tile) {
 // first persistent version recomputed shuffles and 64-bit address math per stage and was bound by
 // instruction issue in these four warps (profiles/r1_conv_ablation.txt).
 struct GatherSlots {
-  const __half* p128[8];
-  const __half* p64[4];
-  uint32_t off128[8];
+  const char* base128;        // in + this lane's 16-byte column of a 128-byte row chunk
+  const char* base64;         // in + first tail channel + this lane's column of a 64-byte row chunk
+  uint32_t o128[8];           // byte offset of the source row of each slot, kNoRow = no neighbour
+  uint32_t o64[4];
+  uint32_t off128[8];         // swizzled shared-memory offsets (constant)
   uint32_t off64[4];
-  uint32_t ok128, ok64;
 };
+constexpr uint32_t kNoRow = 0xFFFFFFFFu;
 
-__device__ __forceinline__ void slots_init(GatherSlots& g, int warp, int lane) {
+__device__ __forceinline__ void slots_init(GatherSlots& g, const Params& p, int warp, int lane) {
+  g.base128 = reinterpret_cast<const char*>(p.in) + (lane & 7) * 16;
+  g.base64 = reinterpret_cast<const char*>(p.in) + p.n64 * 128 + (lane & 3) * 16;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = warp * 32 + i * 4 + (lane >> 3);          // 0 .. 128T-1
@@ -166,36 +171,36 @@ __device__ __forceinline__ void slots_init(GatherSlots& g, int warp, int lane) {
   }
 }
 
+// my_src = map entry of row (warp * 32 + lane).  Rows are addressed by 32-bit byte offsets from
+// `in` (the launcher routes inputs of 4 GiB and more to the v2 kernel): one multiply per lane, then
+// one shuffle per slot - the 64-bit pointer per slot of the first version was 9 instructions per
+// slot and made these warps issue-bound (profiles/r1_conv_ablation.txt).
 __device__ __forceinline__ void slots_set_rows(GatherSlots& g, const Params& p, int32_t my_src, int lane) {
-  g.ok128 = 0;
-  g.ok64 = 0;
+  const uint32_t my_off = my_src >= 0 ? (uint32_t)my_src * (uint32_t)(p.c_red * 2) : kNoRow;
   if (p.n64) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int32_t src = __shfl_sync(0xffffffffu, my_src, i * 4 + (lane >> 3));
-      g.p128[i] = p.in + (src >= 0 ? (int64_t)src * p.c_red : 0) + (lane & 7) * 8;
-      g.ok128 |= (src >= 0 ? 1u : 0u) << i;
-    }
+    for (int i = 0; i < 8; ++i) g.o128[i] = __shfl_sync(0xffffffffu, my_off, i * 4 + (lane >> 3));
   }
   if (p.tail32) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int32_t src = __shfl_sync(0xffffffffu, my_src, i * 8 + (lane >> 2));
-      g.p64[i] = p.in + (src >= 0 ? (int64_t)src * p.c_red : 0) + p.n64 * 64 + (lane & 3) * 8;
-      g.ok64 |= (src >= 0 ? 1u : 0u) << i;
-    }
+    for (int i = 0; i < 4; ++i) g.o64[i] = __shfl_sync(0xffffffffu, my_off, i * 8 + (lane >> 2));
   }
 }
 
 __device__ __forceinline__ void gather_wide(const GatherSlots& g, uint32_t a_base, int col) {
+  const char* b = g.base128 + col * 2;
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-    cp_async16(a_base + g.off128[i], g.p128[i] + col, ((g.ok128 >> i) & 1u) ? 16u : 0u);
+  for (int i = 0; i < 8; ++i) {
+    const bool ok = g.o128[i] != kNoRow;
+    cp_async16(a_base + g.off128[i], b + (ok ? g.o128[i] : 0u), ok ? 16u : 0u);
+  }
 }
 __device__ __forceinline__ void gather_tail(const GatherSlots& g, uint32_t a_base) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    cp_async16(a_base + g.off64[i], g.p64[i], ((g.ok64 >> i) & 1u) ? 16u : 0u);
+  for (int i = 0; i < 4; ++i) {
+    const bool ok = g.o64[i] != kNoRow;
+    cp_async16(a_base + g.off64[i], g.base64 + (ok ? g.o64[i] : 0u), ok ? 16u : 0u);
+  }
 }
 
 __device__ __forceinline__ int32_t load_src(const Params& p, int k, int64_t r) {
@@ -256,30 +261,58 @@ __global__ void __launch_bounds__(128 * T + 192) gather_gemm_tc3_kernel(
     // ================================================================ A producers
     Ring ring(S);
     GatherSlots g;
-    slots_init(g, warp, lane);
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const KMask amask = load_mask_t<T>(p, tile);
-      const int64_t my_row = (int64_t)tile * kRows + warp * 32 + lane;
-      int k = next_active(amask, -1, p.kvol);
-      int32_t nxt = k < p.kvol ? load_src(p, k, my_row) : -1;
-      while (k < p.kvol) {
-        slots_set_rows(g, p, nxt, lane);
-        const int kn = next_active(amask, k, p.kvol);
-        if (kn < p.kvol) nxt = load_src(p, kn, my_row);        // prefetch the next offset's map
-        for (int c = 0; c < p.n64; ++c) {
-          if (ring.wraps > 0) mbar_wait(smem_u32(&s_empty[ring.s]), (ring.wraps - 1) & 1);
-          gather_wide(g, smem_base + ring.s * p.stage_stride, c * 64);
-          cp_async_mbar_arrive_noinc(smem_u32(&s_full[ring.s]));
-          ring.advance();
-        }
-        if (p.tail32) {
-          if (ring.wraps > 0) mbar_wait(smem_u32(&s_empty[ring.s]), (ring.wraps - 1) & 1);
-          gather_tail(g, smem_base + ring.s * p.stage_stride);
-          cp_async_mbar_arrive_noinc(smem_u32(&s_full[ring.s]));
-          ring.advance();
-        }
-        k = kn;
+    slots_init(g, p, warp, lane);
+    // The walk over the active (tile, offset) steps is flattened and the map entries are loaded
+    // three steps ahead of the gathers that use them, also across tile boundaries: a step is only
+    // 1-3 pipeline stages, less than the latency of the dependent mask -> index loads.
+    struct Step { int tile, k; KMask m; };
+    auto step_next = [&](Step& it) {
+      while (it.tile < p.n_tiles) {
+        it.k = next_active(it.m, it.k, p.kvol);
+        if (it.k < p.kvol) return;
+        it.tile += gridDim.x;
+        if (it.tile < p.n_tiles) it.m = load_mask_t<T>(p, it.tile);
+        it.k = -1;
       }
+    };
+    auto step_src = [&](const Step& it) -> int32_t {
+      if (it.tile >= p.n_tiles) return -1;
+      if (p.dbg & 16) return (int32_t)(((int64_t)it.tile * kRows + warp * 32 + lane) % p.n_rows);
+      return load_src(p, it.k, (int64_t)it.tile * kRows + warp * 32 + lane);
+    };
+    Step it;
+    it.tile = blockIdx.x;
+    it.k = -1;
+    it.m = KMask{0u, 0u, 0u, 0u};
+    if (it.tile < p.n_tiles) it.m = load_mask_t<T>(p, it.tile);
+    step_next(it);
+    bool live0 = it.tile < p.n_tiles;
+    int32_t s0 = step_src(it);
+    step_next(it);
+    bool live1 = it.tile < p.n_tiles;
+    int32_t s1 = step_src(it);
+    step_next(it);
+    bool live2 = it.tile < p.n_tiles;
+    int32_t s2 = step_src(it);
+    while (live0) {
+      slots_set_rows(g, p, s0, lane);
+      step_next(it);
+      const bool live3 = it.tile < p.n_tiles;
+      const int32_t s3 = step_src(it);
+      for (int c = 0; c < p.n64; ++c) {
+        if (ring.wraps > 0) mbar_wait(smem_u32(&s_empty[ring.s]), (ring.wraps - 1) & 1);
+        if (!(p.dbg & 1)) gather_wide(g, smem_base + ring.s * p.stage_stride, c * 64);
+        cp_async_mbar_arrive_noinc(smem_u32(&s_full[ring.s]));
+        ring.advance();
+      }
+      if (p.tail32) {
+        if (ring.wraps > 0) mbar_wait(smem_u32(&s_empty[ring.s]), (ring.wraps - 1) & 1);
+        if (!(p.dbg & 1)) gather_tail(g, smem_base + ring.s * p.stage_stride);
+        cp_async_mbar_arrive_noinc(smem_u32(&s_full[ring.s]));
+        ring.advance();
+      }
+      s0 = s1; s1 = s2; s2 = s3;
+      live0 = live1; live1 = live2; live2 = live3;
     }
     cp_async_wait<0>();
   } else if (warp == kProdWarps) {
@@ -289,8 +322,10 @@ __global__ void __launch_bounds__(128 * T + 192) gather_gemm_tc3_kernel(
       const uint32_t idesc = make_idesc(n_half);
       Ring ring(S);
       int used = 0;                                     // non-empty tiles so far (accumulator turn)
+      KMask nmask = blockIdx.x < p.n_tiles ? load_mask_t<T>(p, blockIdx.x) : KMask{0u, 0u, 0u, 0u};
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const KMask amask = load_mask_t<T>(p, tile);
+        const KMask amask = nmask;                       // next tile's mask loads during this tile
+        if (tile + (int)gridDim.x < p.n_tiles) nmask = load_mask_t<T>(p, tile + gridDim.x);
         if (!amask.any()) continue;
         const int ab = p.acc_bufs == 2 ? (used & 1) : 0;
         const int turn = p.acc_bufs == 2 ? (used >> 1) : used;   // uses of this accumulator before
@@ -304,7 +339,8 @@ __global__ void __launch_bounds__(128 * T + 192) gather_gemm_tc3_kernel(
             tc_fence_after();
             const uint32_t a_base = smem_base + ring.s * p.stage_stride;
             const uint32_t b_base = a_base + kAStage;
-            if (c < p.n64) {
+            if (p.dbg & 4) {
+            } else if (c < p.n64) {
 #pragma unroll
               for (int kk = 0; kk < 4; ++kk) {
                 const uint64_t bd = make_desc<128>(b_base + kk * 32);
@@ -347,8 +383,10 @@ __global__ void __launch_bounds__(128 * T + 192) gather_gemm_tc3_kernel(
     if (lane == 0) {
       const int n_half = p.c_res > 256 ? p.c_res / 2 : p.c_res;
       Ring ring(S);
+      KMask nmask = blockIdx.x < p.n_tiles ? load_mask_t<T>(p, blockIdx.x) : KMask{0u, 0u, 0u, 0u};
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        const KMask amask = load_mask_t<T>(p, tile);
+        const KMask amask = nmask;
+        if (tile + (int)gridDim.x < p.n_tiles) nmask = load_mask_t<T>(p, tile + gridDim.x);
         for (int k = next_active(amask, -1, p.kvol); k < p.kvol; k = next_active(amask, k, p.kvol)) {
           for (int c = 0; c < n_chunks; ++c) {
             if (ring.wraps > 0) mbar_wait(smem_u32(&s_empty[ring.s]), (ring.wraps - 1) & 1);
@@ -356,11 +394,13 @@ __global__ void __launch_bounds__(128 * T + 192) gather_gemm_tc3_kernel(
             const uint32_t b_base = smem_base + ring.s * p.stage_stride + kAStage;
             const bool wide = c < p.n64;
             const int rowb = wide ? 128 : 64;
-            mbar_arrive_expect_tx(bar, (uint32_t)(p.c_res * rowb));
+            mbar_arrive_expect_tx(bar, (p.dbg & 2) ? 0u : (uint32_t)(p.c_res * rowb));
             const CUtensorMap* tm = wide ? &tm64 : &tm32;
             const int col = wide ? c * 64 : p.n64 * 64;
-            tma_load_2d(b_base, tm, col, k * p.c_res, bar);
-            if (n_half != p.c_res) tma_load_2d(b_base + n_half * rowb, tm, col, k * p.c_res + n_half, bar);
+            if (!(p.dbg & 2)) {
+              tma_load_2d(b_base, tm, col, k * p.c_res, bar);
+              if (n_half != p.c_res) tma_load_2d(b_base + n_half * rowb, tm, col, k * p.c_res + n_half, bar);
+            }
             ring.advance();
           }
         }
@@ -370,19 +410,26 @@ __global__ void __launch_bounds__(128 * T + 192) gather_gemm_tc3_kernel(
     // =================================================================== epilogue
     const int q = warp & 3;                              // TMEM lane quarter this warp may read
     int used = 0;
+    KMask nmask = blockIdx.x < p.n_tiles ? load_mask_t<T>(p, blockIdx.x) : KMask{0u, 0u, 0u, 0u};
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const KMask amask = load_mask_t<T>(p, tile);
+      const KMask amask = nmask;
+      if (tile + (int)gridDim.x < p.n_tiles) nmask = load_mask_t<T>(p, tile + gridDim.x);
       const bool any = amask.any();
       const int ab = p.acc_bufs == 2 ? (used & 1) : 0;
       const int turn = p.acc_bufs == 2 ? (used >> 1) : used;
+      // destination rows first: their load overlaps the wait for the accumulator
+      const int64_t r_t0 = (int64_t)tile * kRows + q * 32 + lane;
+      const int64_t r_t1 = r_t0 + kTileM;
+      const int64_t ro0 = (p.row_perm && r_t0 < p.n_rows) ? (int64_t)__ldg(p.row_perm + r_t0) : r_t0;
+      const int64_t ro1 = (T == 2 && p.row_perm && r_t1 < p.n_rows) ? (int64_t)__ldg(p.row_perm + r_t1) : r_t1;
       if (any) {
         mbar_wait_backoff(smem_u32(&s_acc_full[ab]), turn & 1);   // a whole main loop away: sleep
         tc_fence_after();
       }
 #pragma unroll 1
       for (int t = 0; t < T; ++t) {
-      const int64_t r = (int64_t)tile * kRows + t * kTileM + q * 32 + lane;
-      const int64_t r_out = (p.row_perm && r < p.n_rows) ? (int64_t)__ldg(p.row_perm + r) : r;
+      const int64_t r = t == 0 ? r_t0 : r_t1;
+      const int64_t r_out = t == 0 ? ro0 : ro1;
       const uint32_t t_lane = tmem_base + (uint32_t)((ab * T + t) * p.acc_stride) + ((uint32_t)(q * 32) << 16);
       for (int c0 = 0; c0 < p.c_res; c0 += 16) {
         uint32_t v[16];
@@ -393,7 +440,7 @@ __global__ void __launch_bounds__(128 * T + 192) gather_gemm_tc3_kernel(
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = 0u;
         }
-        if (r < p.n_rows) {
+        if (r < p.n_rows && !(p.dbg & 8)) {
           __align__(16) __half h[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -516,6 +563,11 @@ int launch_gather_gemm_tc3(const void* in, const void* wt, int k, int c_red, int
     stages = budget1 / p.stage_stride;
   }
   if (stages > 8) stages = 8;
+  p.dbg = 0;
+  {
+    const char* ed = getenv("B2S_TC3_DBG");
+    if (ed) p.dbg = atoi(ed);
+  }
   {
     const char* es = getenv("B2S_TC_STAGES");
     if (es && atoi(es) >= 2 && atoi(es) <= 8 && atoi(es) * p.stage_stride <= budget1) {

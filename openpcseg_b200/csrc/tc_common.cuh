@@ -9,6 +9,10 @@ namespace tc {
 constexpr int kTileM = 128;
 constexpr int kProducerThreads = 128;
 constexpr int kThreads = 160;
+// suspend-time hint of mbarrier.try_wait: the waiting thread stays descheduled until the phase
+// completes (or this many ns pass) instead of re-issuing the poll - spinning roles were 1/3 of all
+// issued instructions of the gather-GEMM kernel and compete with the gather warps for issue slots
+constexpr uint32_t kWaitHintNs = 4000;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -24,12 +28,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"
       "}" ::"r"(bar),
-      "r"(parity)
+      "r"(parity), "r"(kWaitHintNs)
       : "memory");
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {

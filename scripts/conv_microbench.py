@@ -45,6 +45,7 @@ def main():
     kmaps = {}
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     print(f"batch {a.batch}: voxels per level {[int(c.shape[0]) for c in levels]}")
+    seen_levels = set()
     for name in a.layers.split(","):
         lv, cin, cout = LAYERS[name]
         c = levels[lv]
@@ -64,6 +65,12 @@ def main():
             "dgrad": lambda: B.conv_gather_gemm(gy, w, gmap, n, True, flip, tile_mask=gmask, row_perm=gperm),
             "wgrad": lambda: B.conv_wgrad(x, gy, 27, pairs, km.nbsizes32, False),
         }
+        if omask is not None and name[:2] not in seen_levels:
+            seen_levels.add(name[:2])
+            steps = sum(bin(v & 0xFFFFFFFF).count("1") for v in omask.cpu().flatten().tolist())
+            tiles = (n + 127) // 128
+            print(f"# {name[:2]}: {tiles} row tiles, {steps} active (tile, offset) steps = "
+                  f"{steps / (27.0 * tiles):.3f} of 27/tile; pairs/step {m / max(steps, 1):.1f} of 128")
         useful = 2.0 * m * cin * cout
         dense = 2.0 * 27 * n * cin * cout
         for kind, fn in runs.items():

@@ -18,3 +18,19 @@ def test_segloss_matches_reference_style_loop():
     mine.backward()
     ref.backward()
     assert (logits.grad - l2.grad).abs().max() < 1e-6
+
+
+def test_segloss_cross_entropy_term_matches_torch():
+    torch.manual_seed(1)
+    logits = torch.randn(5000, 20, requires_grad=True)
+    target = torch.randint(0, 20, (5000,))
+    for eps in (0.0, 0.1):
+        mine = SegLoss(ignore_index=0, label_smoothing=eps, lovasz_weight=0.0)
+        l1 = logits.detach().clone().requires_grad_(True)
+        l2 = logits.detach().clone().requires_grad_(True)
+        a = mine.ce_weight * mine(l1, target)
+        b = torch.nn.CrossEntropyLoss(ignore_index=0, label_smoothing=eps)(l2, target)
+        assert abs(float(a) - float(b)) < 1e-6 * abs(float(b)) + 1e-7
+        a.backward()
+        b.backward()
+        assert (l1.grad - l2.grad).abs().max() < 1e-7
