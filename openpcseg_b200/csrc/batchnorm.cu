@@ -52,8 +52,24 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restric
 #pragma unroll
   for (int j = 0; j < W; ++j) s[j] = q[j] = 0.f;
   if (rl < rows_per_block) {
-    for (int64_t r = (int64_t)blockIdx.x * rows_per_block + rl; r < n;
-         r += (int64_t)gridDim.x * rows_per_block) {
+    // four independent 16-byte loads in flight per thread (one per iteration left this pass at
+    // 3.5 TB/s: latency-bound, profiles/r1_launches_final.txt)
+    const int64_t step = (int64_t)gridDim.x * rows_per_block;
+    int64_t r = (int64_t)blockIdx.x * rows_per_block + rl;
+    for (; r + 3 * step < n; r += 4 * step) {
+      VecT<T> v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u].load(x + (r + u * step) * c + cg * W);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+          const float f = v[u].get(j);
+          s[j] += f;
+          q[j] = fmaf(f, f, q[j]);
+        }
+    }
+    for (; r < n; r += step) {
       VecT<T> v;
       v.load(x + r * c + cg * W);
 #pragma unroll

@@ -21,6 +21,7 @@ from ..torchsparse import nn as spnn
 from ..torchsparse.nn.functional import batch_norm_act
 from ..torchsparse import PointTensor
 from .losses import SegLoss
+from ..torchsparse.operators import _CatFeats
 from .point_voxel import initial_voxelize, voxel_to_point
 
 __all__ = ["MinkUNet", "MinkUNetConfig", "minkunet34_config"]
@@ -156,7 +157,7 @@ class MinkUNet(nn.Module):
         y3 = self._up(self.up3, y2, x1)
         y4 = self._up(self.up4, y3, x0)
         z3 = voxel_to_point(y4, z2)
-        return self.classifier(torch.cat([z1.F, z2.F, z3.F], dim=1))
+        return self.classifier(_CatFeats.apply(z1.F, z2.F, z3.F))
 
     def forward(self, batch_dict):
         logits = self.forward_logits(batch_dict["lidar"])
