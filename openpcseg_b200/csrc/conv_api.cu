@@ -102,7 +102,9 @@ int b2s_conv_wgrad(int32_t dtype, const void* in, int64_t n_in, const void* grad
   const int64_t rows = swap_pairs ? n_in : n_out;
   const int64_t bound = nbmaps ? rows * k : (n_in < n_out ? n_in : n_out);
   const int64_t n_identity = n_in < n_out ? n_in : n_out;
-  if (dtype == B2S_F16 && !force_simt() && tc_wgrad_supported(c_in, c_out)) {
+  // the tensor-core kernel addresses rows by 32-bit byte offsets
+  const bool small = n_in * (int64_t)c_in * 2 < 0xFFFFFF00LL && n_out * (int64_t)c_out * 2 < 0xFFFFFF00LL;
+  if (dtype == B2S_F16 && !force_simt() && small && tc_wgrad_supported(c_in, c_out)) {
     int rc = launch_wgrad_tc(in, grad_out, nbmaps, nbsizes, n_identity, bound, k, c_in, c_out,
                              swap_pairs, grad_w, st);
     if (rc != B2S_OK) return rc;

@@ -439,25 +439,33 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p) {
       const int sub = lane >> 3, chunk = lane & 7;
       const int2* pr = reinterpret_cast<const int2*>(p.pairs);
       const int64_t pair0 = s_start[k];
+      // Rows are addressed by 32-bit byte offsets from x / gy (the dispatcher keeps tensors of 4 GiB
+      // and more on the SIMT kernel): one multiply per pair instead of 64-bit address arithmetic per
+      // 16-byte copy, which made these warps latency-bound on their own instruction stream.
+      constexpr uint32_t kNoRow = 0xFFFFFFFFu;
+      const uint32_t x_row_bytes = (uint32_t)p.c_in * 2u, y_row_bytes = (uint32_t)p.c_out * 2u;
+      const char* x_lane = reinterpret_cast<const char*>(p.x) + ch_base * 2 + chunk * 16;
+      const char* y_lane = reinterpret_cast<const char*>(p.gy) + chunk * 16;
       // Pair indices are fetched two stages per load (lanes 0-15: stage st2, lanes 16-31: stage
       // st2+1; this warp stages rows [warp*16, warp*16+16) of every 64-pair stage) and two such
       // loads ahead of the gathers that consume them, so the index latency is off the issue path.
-      auto load_idx = [&](int st2, int32_t& ii, int32_t& oo) {
-        ii = -1;
-        oo = -1;
+      auto load_idx = [&](int st2, uint32_t& ii, uint32_t& oo) {
+        ii = kNoRow;
+        oo = kNoRow;
         const int st = st2 + (lane >> 4);
         const int64_t q = lo + (int64_t)st * kRows + warp * 16 + (lane & 15);
         if (st < n_stage && q < hi) {
           if (pr) {
             const int2 v = __ldg(pr + pair0 + q);
-            ii = p.swap_pairs ? v.y : v.x;
-            oo = p.swap_pairs ? v.x : v.y;
+            ii = (uint32_t)(p.swap_pairs ? v.y : v.x) * x_row_bytes;
+            oo = (uint32_t)(p.swap_pairs ? v.x : v.y) * y_row_bytes;
           } else {
-            ii = oo = (int32_t)q;
+            ii = (uint32_t)q * x_row_bytes;
+            oo = (uint32_t)q * y_row_bytes;
           }
         }
       };
-      int32_t i0, o0, i1, o1, i2, o2;
+      uint32_t i0, o0, i1, o1, i2, o2;
       load_idx(0, i0, o0);
       load_idx(2, i1, o1);
       for (int st2 = 0; st2 < n_stage; st2 += 2) {
@@ -473,23 +481,22 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p) {
             if (p.dbg & 1) break;
             const int rl = g * 4 + sub;                             // row within the warp's 16
             const int row = warp * 16 + rl;
-            const int32_t i = __shfl_sync(0xffffffffu, i0, h * 16 + rl);
-            const int32_t o = __shfl_sync(0xffffffffu, o0, h * 16 + rl);
+            const uint32_t io = __shfl_sync(0xffffffffu, i0, h * 16 + rl);
+            const uint32_t oo = __shfl_sync(0xffffffffu, o0, h * 16 + rl);
+            const bool vi = io != kNoRow, vo = oo != kNoRow;
+            const char* xa = x_lane + (vi ? io : 0u);
+            const char* ya = y_lane + (vo ? oo : 0u);
             const uint32_t off = swz<128>(row, chunk);
             // A: two 64-channel panels of X
 #pragma unroll
             for (int pn = 0; pn < 2; ++pn) {
-              const int ch = ch_base + pn * 64 + chunk * 8;
-              if (ch < p.c_in)
-                cp_async16(a_base + pn * kPanelBytes + off,
-                           i >= 0 ? p.x + (int64_t)i * p.c_in + ch : p.x, i >= 0 ? 16u : 0u);
+              if (ch_base + pn * 64 + chunk * 8 < p.c_in)
+                cp_async16(a_base + pn * kPanelBytes + off, xa + pn * 128, vi ? 16u : 0u);
             }
             // B: all panels of dY
             for (int pn = 0; pn < b_panels; ++pn) {
-              const int ch = pn * 64 + chunk * 8;
-              if (ch < p.c_out)
-                cp_async16(b_base + pn * kPanelBytes + off,
-                           o >= 0 ? p.gy + (int64_t)o * p.c_out + ch : p.gy, o >= 0 ? 16u : 0u);
+              if (pn * 64 + chunk * 8 < p.c_out)
+                cp_async16(b_base + pn * kPanelBytes + off, ya + pn * 128, vo ? 16u : 0u);
             }
           }
           // the copy engine signals the stage when this thread's gathers have landed
