@@ -237,7 +237,7 @@ int launch_gather_gemm_tc2(const void* in, const void* wt, int k, int c_red, int
                            const int32_t* nbr, const uint32_t* tile_mask, const int32_t* row_perm,
                            int64_t n_rows, const void* bias, void* out, cudaStream_t st);
 
-int launch_gather_gemm_tc3(const void* in, const void* wt, int k, int c_red, int c_res, int flip_k,
+int launch_gather_gemm_tc3(const void* in, int64_t n_src, const void* wt, int k, int c_red, int c_res, int flip_k,
                            const int32_t* nbr, const uint32_t* tile_mask, const int32_t* row_perm,
                            int64_t n_rows, const void* bias, void* out, cudaStream_t st);
 
@@ -289,7 +289,7 @@ int launch_gather_gemm_tc(const void* in, int64_t n_src, const void* weight, int
   // persistent kernel: needs the tile masks, and addresses source rows by 32-bit byte offsets
   const bool small_src = n_src * (int64_t)c_red * 2 < (int64_t)0xFFFFFF00LL;
   if (!use_v1() && !use_v2() && nbr && tile_mask && small_src)
-    return launch_gather_gemm_tc3(in, wt, k, c_red, c_res, flip_k, nbr, tile_mask, row_perm, n_rows, bias,
+    return launch_gather_gemm_tc3(in, n_src, wt, k, c_red, c_res, flip_k, nbr, tile_mask, row_perm, n_rows, bias,
                                   out, st);
   if (!use_v1())
     return launch_gather_gemm_tc2(in, wt, k, c_red, c_res, flip_k, nbr, tile_mask, row_perm, n_rows, bias,

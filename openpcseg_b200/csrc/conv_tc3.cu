@@ -45,6 +45,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
       "l"(tm), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+// Four rows of a 2-D tensor (row indices r0..r3, column c0) land as four consecutive smem rows in the
+// tensor map's swizzle mode; rows outside [0, n_rows) - the map's -1 entries - are zero-filled and
+// still count their bytes on the barrier (checked by scripts/gather4_probe.cu).
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tm, int c0, int r0, int r1, int r2,
+                                            int r3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+      "l"(tm), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
+      : "memory");
+}
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -222,9 +233,14 @@ __device__ __forceinline__ KMask load_mask_t(const Params& p, int ctile) {
   return m;
 }
 
-template <int T>
+// kTmaGather = false: the gather warps copy rows with cp.async (16 bytes per thread and instruction).
+// kTmaGather = true (experimental, B2S_TC_GATHER4=1): the same warps only hand row indices to the TMA
+// unit, four rows per tile::gather4 instruction (ta64 / ta32 describe `in` as a [n_src, c_red] tensor
+// with 64- / 32-channel boxes of one row); no per-row address arithmetic is left on the SM.
+template <int T, bool kTmaGather>
 __global__ void __launch_bounds__(128 * T + 192) gather_gemm_tc3_kernel(
-    const Params p, const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm32) {
+    const Params p, const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm32,
+    const __grid_constant__ CUtensorMap ta64, const __grid_constant__ CUtensorMap ta32) {
   constexpr int kProdWarps = 4 * T;
   constexpr int kRows = kTileM * T;
   constexpr int kAStage = kABytes * T;
@@ -242,7 +258,7 @@ __global__ void __launch_bounds__(128 * T + 192) gather_gemm_tc3_kernel(
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(smem_u32(&s_full[s]), 128 * T + 1);            // gather threads + TMA expect_tx
+      mbar_init(smem_u32(&s_full[s]), kTmaGather ? 1 : 128 * T + 1);   // (gather threads +) TMA expect_tx
       mbar_init(smem_u32(&s_empty[s]), 1);                     // one tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
@@ -295,6 +311,30 @@ __global__ void __launch_bounds__(128 * T + 192) gather_gemm_tc3_kernel(
     bool live2 = it.tile < p.n_tiles;
     int32_t s2 = step_src(it);
     while (live0) {
+      if constexpr (kTmaGather) {
+        // lanes 0-7 fetch rows [warp*32 + 4*lane, +4) of the CTA tile; their map entries sit in lanes
+        // 4*lane .. 4*lane+3 of s0
+        const int q = (lane & 7) * 4;
+        const int r0 = __shfl_sync(0xffffffffu, s0, q), r1 = __shfl_sync(0xffffffffu, s0, q + 1);
+        const int r2 = __shfl_sync(0xffffffffu, s0, q + 2), r3 = __shfl_sync(0xffffffffu, s0, q + 3);
+        const int row = warp * 32 + q;
+        step_next(it);
+        const bool live3 = it.tile < p.n_tiles;
+        const int32_t s3 = step_src(it);
+        for (int c = 0; c < n_chunks; ++c) {
+          if (ring.wraps > 0) mbar_wait(smem_u32(&s_empty[ring.s]), (ring.wraps - 1) & 1);
+          const bool wide = c < p.n64;
+          const uint32_t dst = smem_base + ring.s * p.stage_stride + (uint32_t)(row >> 7) * kABytes +
+                               (uint32_t)(row & 127) * (wide ? 128u : 64u);
+          if (lane < 8 && !(p.dbg & 1))
+            tma_gather4(dst, wide ? &ta64 : &ta32, wide ? c * 64 : p.n64 * 64, r0, r1, r2, r3,
+                        smem_u32(&s_full[ring.s]));
+          ring.advance();
+        }
+        s0 = s1; s1 = s2; s2 = s3;
+        live0 = live1; live1 = live2; live2 = live3;
+        continue;
+      }
       slots_set_rows(g, p, s0, lane);
       step_next(it);
       const bool live3 = it.tile < p.n_tiles;
@@ -394,7 +434,9 @@ __global__ void __launch_bounds__(128 * T + 192) gather_gemm_tc3_kernel(
             const uint32_t b_base = smem_base + ring.s * p.stage_stride + kAStage;
             const bool wide = c < p.n64;
             const int rowb = wide ? 128 : 64;
-            mbar_arrive_expect_tx(bar, (p.dbg & 2) ? 0u : (uint32_t)(p.c_res * rowb));
+            uint32_t tx = (p.dbg & 2) ? 0u : (uint32_t)(p.c_res * rowb);
+            if (kTmaGather && !(p.dbg & 1)) tx += (uint32_t)(kRows * rowb);   // the gathered A rows
+            mbar_arrive_expect_tx(bar, tx);
             const CUtensorMap* tm = wide ? &tm64 : &tm32;
             const int col = wide ? c * 64 : p.n64 * 64;
             if (!(p.dbg & 2)) {
@@ -504,10 +546,41 @@ static bool make_weight_map(CUtensorMap* tm, const void* w, int k, int c_res, in
   return r == CUDA_SUCCESS;
 }
 
+// `in` as a 2-D tensor [n_src rows, c_red columns] with a one-row box of box_cols channels: the shape
+// tile::gather4 wants (four such rows per instruction).
+static bool make_row_map(CUtensorMap* tm, const void* in, int64_t n_src, int c_red, int box_cols) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)c_red, (cuuint64_t)n_src};
+  cuuint64_t strides[1] = {(cuuint64_t)c_red * sizeof(__half)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, 1u};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(in), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   box_cols == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int T, bool G>
+static cudaError_t launch_variant(const Params& p, const CUtensorMap& tm64, const CUtensorMap& tm32,
+                                  const CUtensorMap& ta64, const CUtensorMap& ta32, int grid, size_t smem,
+                                  cudaStream_t st) {
+  static size_t opted_in = 0;                      // per instantiation
+  if (smem > opted_in) {
+    cudaError_t e = cudaFuncSetAttribute(gather_gemm_tc3_kernel<T, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    opted_in = smem;
+  }
+  gather_gemm_tc3_kernel<T, G><<<grid, 128 * T + 192, smem, st>>>(p, tm64, tm32, ta64, ta32);
+  return cudaSuccess;
+}
+
 }  // namespace tc3
 
 // wt: [K][c_res][c_red] fp16 (K-major B operand); nbr and tile_mask must be non-null
-int launch_gather_gemm_tc3(const void* in, const void* wt, int k, int c_red, int c_res, int flip_k,
+int launch_gather_gemm_tc3(const void* in, int64_t n_src, const void* wt, int k, int c_red, int c_res, int flip_k,
                            const int32_t* nbr, const uint32_t* tile_mask, const int32_t* row_perm,
                            int64_t n_rows, const void* bias, void* out, cudaStream_t st) {
   using namespace tc3;
@@ -578,20 +651,29 @@ int launch_gather_gemm_tc3(const void* in, const void* wt, int k, int c_red, int
   B2S_REQUIRE(stages >= 2, B2S_ERR_UNSUPPORTED, "b2s_conv_gather_gemm: tile does not fit (C=%d)", c_res);
   p.stages = stages;
   const size_t smem = (size_t)stages * p.stage_stride + 1024;
-  static size_t smem_opt_in[3] = {0, 0, 0};
-  if (smem > smem_opt_in[T]) {
-    cudaError_t e = T == 2 ? cudaFuncSetAttribute(gather_gemm_tc3_kernel<2>,
-                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                           : cudaFuncSetAttribute(gather_gemm_tc3_kernel<1>,
-                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    B2S_REQUIRE(e == cudaSuccess, B2S_ERR_CUDA, "b2s_conv_gather_gemm: cannot opt in to %zu B smem: %s",
-                smem, cudaGetErrorString(e));
-    smem_opt_in[T] = smem;
+  // experimental: rows fetched by the TMA unit (tile::gather4) instead of cp.async, see the kernel
+  static const bool gather4 = [] {
+    const char* e = getenv("B2S_TC_GATHER4");
+    return e && e[0] == '1';
+  }();
+  CUtensorMap ta64, ta32;
+  memset(&ta64, 0, sizeof(ta64));
+  memset(&ta32, 0, sizeof(ta32));
+  if (gather4) {
+    if (p.n64) B2S_REQUIRE(make_row_map(&ta64, in, n_src, c_red, 64), B2S_ERR_CUDA,
+                           "b2s_conv_gather_gemm: cuTensorMapEncodeTiled failed (rows, 64-wide)");
+    if (p.tail32) B2S_REQUIRE(make_row_map(&ta32, in, n_src, c_red, 32), B2S_ERR_CUDA,
+                              "b2s_conv_gather_gemm: cuTensorMapEncodeTiled failed (rows, 32-wide)");
   }
   int grid = sm_count() * ctas_per_sm;
   if (grid > p.n_tiles) grid = p.n_tiles;
-  if (T == 2) gather_gemm_tc3_kernel<2><<<grid, 128 * 2 + 192, smem, st>>>(p, tm64, tm32);
-  else gather_gemm_tc3_kernel<1><<<grid, 128 + 192, smem, st>>>(p, tm64, tm32);
+  cudaError_t e;
+  if (T == 2) e = gather4 ? launch_variant<2, true>(p, tm64, tm32, ta64, ta32, grid, smem, st)
+                          : launch_variant<2, false>(p, tm64, tm32, ta64, ta32, grid, smem, st);
+  else e = gather4 ? launch_variant<1, true>(p, tm64, tm32, ta64, ta32, grid, smem, st)
+                   : launch_variant<1, false>(p, tm64, tm32, ta64, ta32, grid, smem, st);
+  B2S_REQUIRE(e == cudaSuccess, B2S_ERR_CUDA, "b2s_conv_gather_gemm: cannot opt in to %zu B smem: %s", smem,
+              cudaGetErrorString(e));
   return B2S_OK;
 }
 
