@@ -12,11 +12,17 @@
 //   * one "full" barrier per stage (128 gather arrivals + the TMA transaction bytes) and one
 //     "empty" barrier (one tcgen05.commit): the MMA thread does 1 wait + 1 commit per stage.
 //
-// Revision 3b - weight reuse.  Measured on v3 (profiles/r1_conv_ablation.txt): every layer ran at
-// ~5.8-6.2 TB/s of L2->SM weight traffic (each 128-row tile re-streams all K weight slices), i.e.
-// the kernel was bound by L2 bandwidth on WEIGHTS, not by gathers or MMAs.  A CTA therefore owns
-// T = 2 row tiles (256 rows): one TMA weight tile per stage now feeds two MMAs (rows 0-127 and
-// 128-255, separate TMEM accumulators), halving the weight bytes per output row.
+// Revision 3b - T = 2 row tiles (256 rows) per CTA share each TMA weight tile (two MMAs, separate TMEM
+// accumulators).  It was motivated by a first reading of the v3 profile (5.8-6.2 TB/s of L2->SM reads,
+// 2/3 of them weights); the later skeleton ablation (all copies, MMAs and stores off: 70 % of the time
+// remains) showed the limiter is the instruction stream of the gather warps per (tile, offset) step, not
+// L2 bandwidth, which is why T = 2 only pays where a step is a single 32-channel stage (C_res <= 32).
+//
+// Revision 3e/3f - tiles are composed by neighbourhood pattern (row_perm from b2s_tile_order_key: 25 % of
+// the (tile, offset) steps stay active at stride 1), the walk over active steps is flattened with the
+// map entries prefetched three steps ahead, source rows are addressed by 32-bit byte offsets, waiting
+// roles use try_wait suspend hints.  An experimental variant hands the row gathers to the TMA unit
+// (tile::gather4, kTmaGather).
 //
 // Warp roles (6 + 4T warps): 0..4T-1 gather producers (cp.async 16 B, zero-fill, SW128 / SW64 tiles),
 // 4 MMA issuer (+ TMEM alloc), 5 TMA weight-tile producer, 6-9 epilogue (TMEM -> fp16 rows).
@@ -613,8 +619,8 @@ int launch_gather_gemm_tc3(const void* in, int64_t n_src, const void* wt, int k,
   p.acc_stride = stride;
   // T = 2 row tiles per CTA share every weight tile.  Measured (profiles/r1_conv_microbench_v3.txt):
   // a win only for the narrowest layers (C_res <= 32: 175 -> 122 us); for C_res >= 64 two
-  // independent 128-row CTAs per SM are faster than one 256-row CTA (the shared-memory write +
-  // read volume of the mostly-empty gathered tiles, not the weight stream, is what saturates).
+  // independent 128-row CTAs per SM are faster than one 256-row CTA (the gather warps' instruction
+  // stream per (tile, offset) step is the limiter, and the union of two tiles' masks adds steps).
   int T = stride <= 32 ? 2 : 1;
   {
     const char* et = getenv("B2S_TC_T");
