@@ -22,7 +22,7 @@ int launch_gather_gemm_tc(const void* in, int64_t n_src, const void* weight, int
                           size_t ws_bytes, cudaStream_t st);
 size_t tc_gather_gemm_workspace(int k, int c_in, int c_out);
 bool tc_wgrad_supported(int c_in, int c_out);
-int launch_wgrad_tc(const void* in, const void* gout, const int32_t* nbmaps,
+int launch_wgrad_tc(const void* in, int64_t n_in, const void* gout, int64_t n_out, const int32_t* nbmaps,
                     const int32_t* nbsizes, int64_t n_identity, int64_t n_pairs_bound, int k,
                     int c_in, int c_out, int swap_pairs, float* gw, cudaStream_t st);
 
@@ -105,7 +105,7 @@ int b2s_conv_wgrad(int32_t dtype, const void* in, int64_t n_in, const void* grad
   // the tensor-core kernel addresses rows by 32-bit byte offsets
   const bool small = n_in * (int64_t)c_in * 2 < 0xFFFFFF00LL && n_out * (int64_t)c_out * 2 < 0xFFFFFF00LL;
   if (dtype == B2S_F16 && !force_simt() && small && tc_wgrad_supported(c_in, c_out)) {
-    int rc = launch_wgrad_tc(in, grad_out, nbmaps, nbsizes, n_identity, bound, k, c_in, c_out,
+    int rc = launch_wgrad_tc(in, n_in, grad_out, n_out, nbmaps, nbsizes, n_identity, bound, k, c_in, c_out,
                              swap_pairs, grad_w, st);
     if (rc != B2S_OK) return rc;
   } else if (dtype == B2S_F16) {

@@ -18,6 +18,9 @@
 // algorithmic bytes = 2*C_red*M (gathered rows) + 2*C_res*N_rows + 4*K*N_rows + 2*K*C_in*C_out.
 #include <stdlib.h>
 
+#include <cuda.h>
+#include <string.h>
+
 #include "tc_common.cuh"
 
 namespace b2s {
@@ -378,7 +381,22 @@ struct WParams {
   int dbg;                // ablation: bit0 no gathers, bit1 no MMAs, bit2 no epilogue reds
 };
 
-__global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p) {
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tm, int c0, int r0, int r1, int r2,
+                                            int r3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
+      "l"(tm), "r"(c0), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
+      : "memory");
+}
+
+// kTma = false: rows copied with cp.async.  kTma = true (experimental, B2S_WG_GATHER4=1, not yet run on
+// hardware): the producer warps hand the pair indices to the TMA unit, four rows per tile::gather4
+// (tmx / tmy describe x and gy as [rows, channels] tensors with a one-row, 64-channel box; channels past
+// the tensor width are zero-filled), and the stage barrier counts bytes instead of thread arrivals.
+template <bool kTma>
+__global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p, const __grid_constant__ CUtensorMap tmx,
+                                                            const __grid_constant__ CUtensorMap tmy) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int b_panels = (p.c_out + 63) / 64;
@@ -395,7 +413,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p) {
   const int S = p.stages;
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(smem_u32(&s_full[s]), kProducerThreads);
+      mbar_init(smem_u32(&s_full[s]), kTma ? 1 : kProducerThreads);
       mbar_init(smem_u32(&s_empty[s]), 1);
     }
     mbar_init(smem_u32(&s_acc), 1);
@@ -457,11 +475,11 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p) {
         if (st < n_stage && q < hi) {
           if (pr) {
             const int2 v = __ldg(pr + pair0 + q);
-            ii = (uint32_t)(p.swap_pairs ? v.y : v.x) * x_row_bytes;
-            oo = (uint32_t)(p.swap_pairs ? v.x : v.y) * y_row_bytes;
+            ii = (uint32_t)(p.swap_pairs ? v.y : v.x) * (kTma ? 1u : x_row_bytes);
+            oo = (uint32_t)(p.swap_pairs ? v.x : v.y) * (kTma ? 1u : y_row_bytes);
           } else {
-            ii = (uint32_t)q * x_row_bytes;
-            oo = (uint32_t)q * y_row_bytes;
+            ii = (uint32_t)q * (kTma ? 1u : x_row_bytes);
+            oo = (uint32_t)q * (kTma ? 1u : y_row_bytes);
           }
         }
       };
@@ -476,6 +494,28 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p) {
           if (rwraps > 0) mbar_wait(smem_u32(&s_empty[rs]), (rwraps - 1) & 1);
           const uint32_t a_base = smem_base + rs * stage_stride;
           const uint32_t b_base = a_base + a_bytes;
+          if constexpr (kTma) {
+            // slots: the 1-2 live X panels, then the dY panels; lane = (slot % 8) * 4 + j fetches rows
+            // [warp*16 + 4j, +4) of its slot(s); kNoRow is -1 as a coordinate: out of range -> zeros
+            const int a_used = (p.c_in - ch_base > 64) ? 2 : 1;
+            const int n_slots = a_used + b_panels;
+            const uint32_t bar = smem_u32(&s_full[rs]);
+            if (warp == 0 && lane == 0)
+              mbar_arrive_expect_tx(bar, (p.dbg & 1) ? 0u : (uint32_t)(n_slots * kPanelBytes));
+            const int j = lane & 3, src = h * 16 + j * 4;
+            const int xi0 = (int)__shfl_sync(0xffffffffu, i0, src), xi1 = (int)__shfl_sync(0xffffffffu, i0, src + 1);
+            const int xi2 = (int)__shfl_sync(0xffffffffu, i0, src + 2), xi3 = (int)__shfl_sync(0xffffffffu, i0, src + 3);
+            const int yo0 = (int)__shfl_sync(0xffffffffu, o0, src), yo1 = (int)__shfl_sync(0xffffffffu, o0, src + 1);
+            const int yo2 = (int)__shfl_sync(0xffffffffu, o0, src + 2), yo3 = (int)__shfl_sync(0xffffffffu, o0, src + 3);
+            const uint32_t row_off = (uint32_t)(warp * 16 + j * 4) * 128u;
+            for (int slot = lane >> 2; slot < n_slots && !(p.dbg & 1); slot += 8) {
+              if (slot < a_used)
+                tma_gather4(a_base + slot * kPanelBytes + row_off, &tmx, ch_base + slot * 64, xi0, xi1, xi2, xi3, bar);
+              else
+                tma_gather4(b_base + (slot - a_used) * kPanelBytes + row_off, &tmy, (slot - a_used) * 64, yo0, yo1,
+                            yo2, yo3, bar);
+            }
+          } else {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             if (p.dbg & 1) break;
@@ -503,6 +543,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p) {
           asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(
                            smem_u32(&s_full[rs]))
                        : "memory");
+          }
           if (++rs == S) { rs = 0; ++rwraps; }
         }
         i0 = i1; o0 = o1;
@@ -574,7 +615,24 @@ bool tc_wgrad_supported(int c_in, int c_out) {
   return true;
 }
 
-int launch_wgrad_tc(const void* in, const void* gout, const int32_t* nbmaps,
+bool tc_make_row_map(CUtensorMap* tm, const void* base, int64_t rows, int cols, int box_cols);   // conv_tc3.cu
+
+namespace tcw {
+template <bool kTma>
+static cudaError_t launch_wgrad_variant(const WParams& p, const CUtensorMap& tmx, const CUtensorMap& tmy, int grid,
+                                        size_t smem, cudaStream_t st) {
+  static size_t opted_in = 0;
+  if (smem > opted_in) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<kTma>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    opted_in = smem;
+  }
+  wgrad_tc_kernel<kTma><<<grid, kThreads, smem, st>>>(p, tmx, tmy);
+  return cudaSuccess;
+}
+}  // namespace tcw
+
+int launch_wgrad_tc(const void* in, int64_t n_in, const void* gout, int64_t n_out, const int32_t* nbmaps,
                     const int32_t* nbsizes, int64_t n_identity, int64_t n_pairs_bound, int k,
                     int c_in, int c_out, int swap_pairs, float* gw, cudaStream_t st) {
   using namespace tcw;
@@ -617,11 +675,26 @@ int launch_wgrad_tc(const void* in, const void* gout, const int32_t* nbmaps,
   if (unit > 256 * kRows) unit = 256 * kRows;
   p.unit_pairs = (int)unit;
   const size_t smem = (size_t)stages * stage + 1024;
-  cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int64_t max_units = (n_pairs_bound / unit + k) * p.m_tiles;
   const int64_t slots = (int64_t)sms * (two_per_sm ? 2 : 1);
   int grid = (int)(max_units < slots ? (max_units < 1 ? 1 : max_units) : slots);
-  wgrad_tc_kernel<<<grid, kThreads, smem, st>>>(p);
+  // experimental: both operands fetched by the TMA unit (tile::gather4), see the kernel
+  static const bool gather4 = [] {
+    const char* e = getenv("B2S_WG_GATHER4");
+    return e && e[0] == '1';
+  }();
+  CUtensorMap tmx, tmy;
+  memset(&tmx, 0, sizeof(tmx));
+  memset(&tmy, 0, sizeof(tmy));
+  if (gather4) {
+    B2S_REQUIRE(c_in % 8 == 0 && c_out % 8 == 0 && tc_make_row_map(&tmx, in, n_in, c_in, 64) &&
+                    tc_make_row_map(&tmy, gout, n_out, c_out, 64),
+                B2S_ERR_CUDA, "b2s_conv_wgrad: cuTensorMapEncodeTiled failed");
+  }
+  cudaError_t e = gather4 ? launch_wgrad_variant<true>(p, tmx, tmy, grid, smem, st)
+                          : launch_wgrad_variant<false>(p, tmx, tmy, grid, smem, st);
+  B2S_REQUIRE(e == cudaSuccess, B2S_ERR_CUDA, "b2s_conv_wgrad: cannot opt in to %zu B smem: %s", smem,
+              cudaGetErrorString(e));
   return B2S_OK;
 }
 

@@ -29,10 +29,6 @@ using namespace tc;
 constexpr int kThreads2 = 192;
 constexpr int kABytes = kTileM * 128;       // A region of a stage (SW128 worst case)
 
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1,
                                             uint32_t bar) {
   asm volatile(

@@ -39,10 +39,6 @@ using namespace tc;
 
 constexpr int kABytes = kTileM * 128;
 
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-               : "memory");
-}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1,
                                             uint32_t bar) {
   asm volatile(
@@ -584,6 +580,11 @@ static cudaError_t launch_variant(const Params& p, const CUtensorMap& tm64, cons
 }
 
 }  // namespace tc3
+
+// shared with the weight-gradient kernel (conv_tc.cu)
+bool tc_make_row_map(CUtensorMap* tm, const void* base, int64_t rows, int cols, int box_cols) {
+  return tc3::make_row_map(tm, base, rows, cols, box_cols);
+}
 
 // wt: [K][c_res][c_red] fp16 (K-major B operand); nbr and tile_mask must be non-null
 int launch_gather_gemm_tc3(const void* in, int64_t n_src, const void* wt, int k, int c_red, int c_res, int flip_k,
