@@ -1,8 +1,11 @@
 """TEST INFRASTRUCTURE ONLY - numpy restatement of the reference's per-scan preprocessing.
 
 Checks ``openpcseg_b200/frontend.py``.  Only tests may import this module.  Each
-function follows the reference lines cited; parity of these restatements is unpinned by the reference
-(it has no tests for its datasets) - they are line-by-line restatements of short numpy programs.
+function follows the reference lines cited.  Pinning: the reference has no tests for its datasets, so
+tests/golden/frontend.npz freezes outputs of the reference's OWN functions run in the build container
+(sparse_quantize, cart2polar, voxelize_with_label, get_range_image; generator
+tests/golden/make_golden_frontend.py) and tests/test_frontend_cpu.py checks these restatements and the product
+against them.
 """
 import numpy as np
 

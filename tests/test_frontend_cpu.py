@@ -76,3 +76,44 @@ def test_front_end_reproduces_the_benchmark_scan():
     np.testing.assert_array_equal(out["lidar"].C.numpy(), scan["coords"])
     np.testing.assert_array_equal(out["lidar"].F.numpy(), scan["feats"])
     np.testing.assert_array_equal(out["inverse_map"].F.numpy(), np.arange(scan["coords"].shape[0]))
+
+
+# ----------------------------------------------------- pinned to outputs of the reference's own functions
+def _golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "frontend.npz"))
+
+
+def test_sparse_quantize_matches_reference_output():
+    from openpcseg_b200.torchsparse.utils.quantize import sparse_quantize
+    g = _golden()
+    vox, idx, inv = sparse_quantize(g["q_pts"], 0.25, return_index=True, return_inverse=True)
+    np.testing.assert_array_equal(vox, g["q_vox"])
+    np.testing.assert_array_equal(idx, g["q_idx"])
+    np.testing.assert_array_equal(inv, g["q_inv"])
+
+
+def test_cylinder_pieces_match_reference_output():
+    g = _golden()
+    vc, vl, inds, inv = R.voxelize_with_label_ref(g["c_coords"], g["c_labels"], 20)          # the restatement
+    for got, key in ((vc, "c_vcoords"), (vl, "c_vlabels"), (inds, "c_inds"), (inv, "c_inverse")):
+        np.testing.assert_array_equal(got, g[key], err_msg=key)
+    gc, gl, gi, gn = frontend.voxelize_with_label(torch.from_numpy(g["c_coords"]), torch.from_numpy(g["c_labels"]), 20)
+    for got, key in ((gc, "c_vcoords"), (gl, "c_vlabels"), (gi, "c_inds"), (gn, "c_inverse")):
+        np.testing.assert_array_equal(got.numpy(), g[key], err_msg=key)
+    # cart2polar (radians) against the polar part of the tensor program (degrees)
+    args = dict(grid_size=[480, 360, 32], min_bound=[0.0, -180.0, -4.0], max_bound=[50.0, 180.0, 2.0], num_classes=20)
+    out = frontend.cylinder_scan(torch.from_numpy(g["c_scan"]), torch.from_numpy(g["c_labels"]), **args)
+    pol = g["c_polar"].copy()
+    pol[:, 1] = pol[:, 1] / np.pi * 180.0
+    np.testing.assert_allclose(out["point_feature"][:, 3:6].numpy(), pol.astype(np.float32), rtol=0, atol=2e-5)
+
+
+def test_range_projection_matches_reference_output():
+    g = _golden()
+    img, pxpy = frontend.range_projection(torch.from_numpy(g["r_points"]), float(g["r_yaw_offset"]))
+    np.testing.assert_array_equal(pxpy.numpy(), g["r_pxpy"])
+    np.testing.assert_array_equal(img.numpy(), g["r_image"])
+    img_r, pxpy_r = R.range_projection_ref(g["r_points"], float(g["r_yaw_offset"]))
+    np.testing.assert_array_equal(img_r, g["r_image"])
+    np.testing.assert_array_equal(pxpy_r, g["r_pxpy"])
