@@ -34,3 +34,20 @@ def test_segloss_cross_entropy_term_matches_torch():
         a.backward()
         b.backward()
         assert (l1.grad - l2.grad).abs().max() < 1e-7
+
+
+def test_segloss_matches_reference_loss_outputs():
+    """tests/golden/loss.npz: CE + Lovasz of the reference's own functions (make_golden_loss.py)."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "loss.npz"))
+    for tag in ("a", "b"):
+        logits = torch.from_numpy(g[f"{tag}_logits"]).requires_grad_(True)
+        target = torch.from_numpy(g[f"{tag}_target"])
+        crit = SegLoss(ignore_index=0, label_smoothing=float(g[f"{tag}_smoothing"]))
+        loss = crit(logits, target)
+        assert abs(float(loss) - float(g[f"{tag}_loss"])) < 2e-6 * abs(float(g[f"{tag}_loss"]))
+        loss.backward()
+        assert float((logits.grad - torch.from_numpy(g[f"{tag}_grad"])).abs().max()) < 1e-7
+        only_lov = SegLoss(ignore_index=0, label_smoothing=0.0, ce_weight=0.0)(logits.detach(), target)
+        assert abs(float(only_lov) - float(g[f"{tag}_lovasz"])) < 2e-6 * abs(float(g[f"{tag}_lovasz"]))
