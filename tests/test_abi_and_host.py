@@ -142,3 +142,16 @@ def test_install_as_torchsparse():
     assert hasattr(torchsparse, "cat") and hasattr(torchsparse.backend, "convolution_forward_cuda")
     for k in [k for k in sys.modules if k == "torchsparse" or k.startswith("torchsparse.")]:
         del sys.modules[k]
+
+
+def test_minkunet_state_dict_matches_reference_inventory():
+    """tests/golden/model_keys.json: key -> shape of the reference's MinkUNet-34 cr1.0 (make_golden_model.py);
+    a reference checkpoint therefore loads with strict=True."""
+    import json
+    from openpcseg_b200.segmentors import MinkUNet, minkunet34_config
+    with open(os.path.join(os.path.dirname(__file__), "golden", "model_keys.json")) as f:
+        g = json.load(f)
+    net = MinkUNet(minkunet34_config())
+    mine = {k: list(v.shape) for k, v in net.state_dict().items()}
+    assert mine == g["state_dict"]
+    assert sum(p.numel() for p in net.parameters()) == g["n_params"] == 37882900
