@@ -22,6 +22,9 @@ def install_as_torchsparse() -> None:
     from . import backend
     sys.modules["torchsparse.backend"] = backend
     pkg.backend = backend
+    # RPVNet's range-image ops (`import range_utils.nn.functional as rnf`, rpvnet.py:26)
+    for name in ["", ".nn", ".nn.functional"]:
+        sys.modules["range_utils" + name] = importlib.import_module("openpcseg_b200.range_utils" + name)
     try:                                  # Cylinder3D's scatter_max when torch_scatter is not installed
         importlib.import_module("torch_scatter")
     except ImportError:

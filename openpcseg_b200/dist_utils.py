@@ -18,8 +18,8 @@ def env_rank_world() -> Tuple[int, int, int]:
 def scan_seeds(rank: int, pool_index: int, batch: int) -> List[int]:
     """Seeds of the scans rank `rank` processes in pool slot `pool_index`: disjoint across
     ranks and slots (weak scaling: every rank gets `batch` scans of its own)."""
-    assert batch <= 10 and pool_index < 100
-    return [1000 * rank + 10 * pool_index + i for i in range(batch)]
+    assert batch <= 20 and pool_index < 50
+    return [1000 * rank + 20 * pool_index + i for i in range(batch)]
 
 
 def max_over_ranks(value_ms: float, device) -> float:

@@ -412,7 +412,10 @@ def batch_norm_act(x: torch.Tensor, bn: torch.nn.modules.batchnorm._BatchNorm, r
         torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
     if (not bn.training) or sync or not bn.track_running_stats or bn.momentum is None \
             or not B.bn_supported(x) or (residual is not None and residual.dtype != x.dtype):
-        y = bn(x)
+        # the dense implementation of the module's class on the [N, C] rows (the sparse wrappers'
+        # own forward expects a SparseTensor)
+        dense = torch.nn.SyncBatchNorm if isinstance(bn, torch.nn.SyncBatchNorm) else torch.nn.BatchNorm1d
+        y = dense.forward(bn, x)
         if residual is not None:
             y = y + residual
         return torch.relu(y) if relu else y
