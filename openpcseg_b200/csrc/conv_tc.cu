@@ -436,7 +436,9 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p, con
   tc_fence_after();
   const uint32_t tmem_acc = s_tmem;
   const int total_units = s_units[p.kvol] * p.m_tiles;
-  const int n_half = p.c_out > 256 ? p.c_out / 2 : p.c_out;
+  // C_out > 256: two MMAs per K step, N = 256 and N = C_out - 256 (the B operand of the second one starts
+  // at the fifth 64-channel panel, so any C_out % 16 == 0 up to 512 works, e.g. 448 of RPVNet cr1.75)
+  const int n_first = p.c_out > 256 ? 256 : p.c_out;
 
   // ring position shared by the roles (each role advances its own copy identically)
   int rs = 0, rwraps = 0;
@@ -570,7 +572,8 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p, con
       tc_fence_before();
     } else {
       // --------------------------------------------------------------- MMA issuer
-      const uint32_t idesc = make_idesc_mn(n_half);
+      const uint32_t idesc = make_idesc_mn(n_first);
+      const uint32_t idesc2 = make_idesc_mn(p.c_out - n_first);
       for (int st = 0; st < n_stage; ++st) {
         mbar_wait(smem_u32(&s_full[rs]), rwraps & 1);
         fence_proxy_async();           // rows were written through the generic proxy (cp.async)
@@ -584,10 +587,10 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p, con
             const uint64_t ad = make_desc_mn(a_base + kk * 2048, kPanelBytes);
             const uint64_t bd = make_desc_mn(b_base + kk * 2048, kPanelBytes);
             umma_f16(tmem_acc, ad, bd, idesc, (st | kk) ? 1u : 0u);
-            if (n_half != p.c_out) {
-              const uint64_t bd2 = make_desc_mn(b_base + (n_half / 64) * kPanelBytes + kk * 2048,
+            if (n_first != p.c_out) {
+              const uint64_t bd2 = make_desc_mn(b_base + (n_first / 64) * kPanelBytes + kk * 2048,
                                                 kPanelBytes);
-              umma_f16(tmem_acc + (uint32_t)n_half, ad, bd2, idesc, (st | kk) ? 1u : 0u);
+              umma_f16(tmem_acc + (uint32_t)n_first, ad, bd2, idesc2, (st | kk) ? 1u : 0u);
             }
           }
           umma_commit(smem_u32(&s_empty[rs]));
@@ -611,8 +614,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p, con
 bool tc_wgrad_supported(int c_in, int c_out) {
   if (c_in % 8 != 0 || c_in < 8) return false;
   if (c_out % 16 != 0 || c_out < 16 || c_out > 512) return false;
-  if (c_out > 256 && ((c_out / 2) % 64 != 0)) return false;   // split needs a panel boundary
-  return true;
+  return true;                                                 // C_out > 256 splits as 256 + rest
 }
 
 bool tc_make_row_map(CUtensorMap* tm, const void* base, int64_t rows, int cols, int box_cols);   // conv_tc3.cu

@@ -236,6 +236,21 @@ def _cast_weight(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return w
 
 
+def _gather_gemm_wide(feats, w, gmap, n_rows, transpose_w, flip, **kw):
+    """conv_gather_gemm with result widths above the kernel's 512 TMEM columns split into column
+    blocks of the weight (e.g. the input gradient of RPVNet's 672 -> 448 decoder conv)."""
+    c_res = w.shape[1] if transpose_w else w.shape[2]
+    if c_res <= 512 or feats.dtype != torch.float16:
+        return B.conv_gather_gemm(feats, w, gmap, n_rows, transpose_w, flip, **kw)
+    n_blk = -(-c_res // 512)
+    step = -(-c_res // (n_blk * 32)) * 32
+    outs = []
+    for c0 in range(0, c_res, step):
+        wb = (w[:, c0:c0 + step, :] if transpose_w else w[:, :, c0:c0 + step]).contiguous()
+        outs.append(B.conv_gather_gemm(feats, wb, gmap, n_rows, transpose_w, flip, **kw))
+    return torch.cat(outs, dim=1)
+
+
 class ConvolutionFunction(Function):
     """out = sum_k gather(in, map_k) @ W[k]  (TS/nn/functional/conv.py:16-119).
 
@@ -250,12 +265,12 @@ class ConvolutionFunction(Function):
         hint = kmap.total_hint()
         if not transposed:
             gmap, mask, perm = kmap.out_gather_map()
-            out = B.conv_gather_gemm(feats, w, gmap, kmap.sizes[1], False, False, pairs_hint=hint,
-                                     tile_mask=mask, row_perm=perm)
+            out = _gather_gemm_wide(feats, w, gmap, kmap.sizes[1], False, False, pairs_hint=hint,
+                                    tile_mask=mask, row_perm=perm)
         else:
             gmap, flip, mask, perm = kmap.in_gather_map()
-            out = B.conv_gather_gemm(feats, w, gmap, kmap.sizes[0], False, flip, pairs_hint=hint,
-                                     tile_mask=mask, row_perm=perm)
+            out = _gather_gemm_wide(feats, w, gmap, kmap.sizes[0], False, flip, pairs_hint=hint,
+                                    tile_mask=mask, row_perm=perm)
         ctx.save_for_backward(feats, weight)
         ctx.kmap, ctx.transposed = kmap, transposed
         return out
@@ -272,12 +287,12 @@ class ConvolutionFunction(Function):
         if ctx.needs_input_grad[0]:
             if not transposed:
                 gmap, flip, mask, perm = kmap.in_gather_map()
-                grad_in = B.conv_gather_gemm(grad_out, w, gmap, kmap.sizes[0], True, flip, pairs_hint=hint,
-                                             tile_mask=mask, row_perm=perm)
+                grad_in = _gather_gemm_wide(grad_out, w, gmap, kmap.sizes[0], True, flip, pairs_hint=hint,
+                                            tile_mask=mask, row_perm=perm)
             else:
                 gmap, mask, perm = kmap.out_gather_map()
-                grad_in = B.conv_gather_gemm(grad_out, w, gmap, kmap.sizes[1], True, False,
-                                             pairs_hint=hint, tile_mask=mask, row_perm=perm)
+                grad_in = _gather_gemm_wide(grad_out, w, gmap, kmap.sizes[1], True, False,
+                                            pairs_hint=hint, tile_mask=mask, row_perm=perm)
         if ctx.needs_input_grad[1]:
             pairs, _ = kmap.pairs()
             grad_w = B.conv_wgrad(feats, grad_out, kmap.kvol, pairs, kmap.nbsizes32, transposed,
@@ -293,7 +308,8 @@ class _DenseConv(Function):
     def forward(ctx, feats, weight):
         feats = feats.contiguous()
         ctx.save_for_backward(feats, weight)
-        return B.conv_gather_gemm(feats, _cast_weight(weight, feats.dtype), None, feats.shape[0], False, False)
+        return _gather_gemm_wide(feats, _cast_weight(weight, feats.dtype).unsqueeze(0), None, feats.shape[0],
+                                 False, False)
 
     @staticmethod
     @once_differentiable
@@ -302,21 +318,22 @@ class _DenseConv(Function):
         grad_out = grad_out.contiguous()
         grad_in = grad_w = None
         if ctx.needs_input_grad[0]:
-            grad_in = B.conv_gather_gemm(grad_out, _cast_weight(weight, feats.dtype), None, feats.shape[0],
-                                         True, False)
+            grad_in = _gather_gemm_wide(grad_out, _cast_weight(weight, feats.dtype).unsqueeze(0), None,
+                                        feats.shape[0], True, False)
         if ctx.needs_input_grad[1]:
             grad_w = B.conv_wgrad(feats, grad_out, 1, None, None, False)[0].to(weight.dtype)
         return grad_in, grad_w
 
 
 def _pad_for_tensor_cores(feats: torch.Tensor, weight: torch.Tensor):
-    """fp16 only: zero-pad C_in to a multiple of 32 and C_out to a multiple of 16 so narrow layers
-    (the 4-channel stem, 20-class heads) run on the tcgen05 kernels instead of the CUDA-core
-    family; zero channels change nothing and autograd slices the gradients back."""
+    """fp16 only: zero-pad C_in and C_out to multiples of 32 so that narrow or odd layers (the 4-channel
+    stem, 20-class heads, the 56/112/168-channel layers of the cr 1.75 models) run on the tcgen05 kernels
+    in all three passes (forward reduces over C_in, the input gradient over C_out) instead of the
+    CUDA-core family; zero channels change nothing and autograd slices the gradients back."""
     if feats.dtype != torch.float16:
         return feats, weight, None
     c_in, c_out = weight.shape[-2], weight.shape[-1]
-    pad_in, pad_out = (-c_in) % 32, (-c_out) % 16
+    pad_in, pad_out = (-c_in) % 32, (-c_out) % 32
     if pad_in == 0 and pad_out == 0:
         return feats, weight, None
     feats = torch.nn.functional.pad(feats, (0, pad_in))
@@ -359,7 +376,9 @@ def conv3d(input: SparseTensor, weight: torch.Tensor,
         out_feats = ConvolutionFunction.apply(feats, weight, kmap, True)
 
     if keep_out is not None:
-        out_feats = out_feats[:, :keep_out]
+        # contiguous: a strided [N, C] view sends torch's batch norm to its generic (non channels-last)
+        # kernels - 14 ms per backward launch on the cr 1.75 models
+        out_feats = out_feats[:, :keep_out].contiguous()
     if bias is not None:
         out_feats = out_feats + bias.to(out_feats.dtype)
 

@@ -5,7 +5,8 @@ build of its bundled torchsparse (oracle/_ref) and freeze their outputs (build c
     python tests/golden/make_golden_ref_models.py  ->  tests/golden/ref_models.npz
 
 Per model (MinkUNet-34 cr1.0, SPVCNN-18 cr1.0, Cylinder3D cy480, RPVNet-34 cr1.75; MODEL block of the
-reference yaml, key-seeded weights from oracle/det_weights.py, train mode = batch statistics, dropout 0):
+reference yaml, key-seeded weights from oracle/det_weights.py, train mode = batch statistics, every
+Dropout / Dropout2d instance set to p = 0 so the outputs are deterministic):
 one synthetic scan (seed 3, 64 beams x 60 azimuths) -> training loss + the logits of the classifier head.
 What is NOT the reference in this arm, and why:
   * ``Tensor.cuda`` is patched to the identity (the models call ``.cuda()`` on targets, rpvnet.py:86, minkunet.py:425);
@@ -63,6 +64,9 @@ def main():
         net = ns.build_model(name)
         net.load_state_dict(fill_(net.state_dict()), strict=True)
         net.train()
+        for m in net.modules():                    # RPVNet's range branch carries Dropout2d(0.2): random
+            if isinstance(m, (torch.nn.Dropout, torch.nn.Dropout2d)):
+                m.p = 0.0
         arrays = make_model_batch(kind, [SEED], n_azimuth=N_AZIMUTH)
         cap = {}
 
