@@ -124,6 +124,23 @@ int b2s_tile_mask(const int32_t* nbr, int32_t k, int64_t n, uint32_t* tile_mask,
  * passing the order as row_perm groups rows with equal patterns into the same 128-row tiles.      */
 int b2s_tile_order_key(const int32_t* nbr, int32_t k, int64_t n, const int32_t* nbsizes,
                        const int32_t* coords, int32_t coord_shift, int64_t* keys, b2s_stream_t stream);
+/* Same, and also emits row_bits uint32 [n]: bit kk of row r <=> nbr[kk][r] >= 0 (k <= 32), which
+ * b2s_tile_steps uses to build tile masks with one read per row.                                     */
+int b2s_tile_order_key_bits(const int32_t* nbr, int32_t k, int64_t n, const int32_t* nbsizes,
+                            const int32_t* coords, int32_t coord_shift, int64_t* keys, uint32_t* row_bits,
+                            b2s_stream_t stream);
+/* Step table of a gather map for the tensor-core convolution (conv_tc4.cu).  Launch row j (j < n) is map
+ * column perm[j] (perm == NULL: j); tiles are `tile_rows` (128 | 256) consecutive launch rows.  Outputs:
+ *   tile_mask  uint32 [tiles][ceil(k/32)]  active offsets of a tile;
+ *   step_start int32 [tiles + 1]           exclusive prefix of the per-tile active-offset counts;
+ *   step_rows  int32 [<= k * tiles * tile_rows]  for step s = step_start[t] + (rank of offset kk among the
+ *              active offsets of tile t), tile row w*32 + i*4 + q is stored at s*tile_rows + w*32 + q*8 + i
+ *              (= nbr[kk][launch row] or -1): the eight rows one gather lane copies are contiguous.
+ * Everything stays on the device (no size leaves it); row_bits (optional, k <= 32) as emitted by
+ * b2s_tile_order_key_bits.  The capacity k*tiles*tile_rows of step_rows is the caller's to provide.   */
+int b2s_tile_steps(const int32_t* nbr, int32_t k, int64_t n, const int32_t* perm, const uint32_t* row_bits,
+                   int32_t tile_rows, uint32_t* tile_mask, int32_t* step_start, int32_t* step_rows,
+                   b2s_stream_t stream);
 
 /* ------------------------------------------------------------ convolution ---
  * replaces convolution_forward_cuda / convolution_backward_cuda
@@ -150,8 +167,29 @@ size_t b2s_conv_workspace_bytes(int32_t dtype, int64_t n_rows, int32_t c_in, int
 int b2s_conv_gather_gemm(int32_t dtype, const void* in, int64_t n_src, const void* weight,
                          int32_t k, int32_t c_in, int32_t c_out, int32_t transpose_w,
                          int32_t flip_k, const int32_t* nbr, const uint32_t* tile_mask,
-                         const int32_t* row_perm, int64_t n_rows, const void* bias, void* out,
-                         void* ws, size_t ws_bytes, b2s_stream_t stream);
+                         const int32_t* row_perm, int64_t n_rows, const void* bias, void* out, void* ws,
+                         size_t ws_bytes, b2s_stream_t stream);
+/* The same contraction driven by a STEP TABLE (b2s_tile_steps) instead of the [K, n] gather map - the
+ * production path of the fp16 tensor-core kernel (conv_tc4.cu): the table lists only the active (tile, offset)
+ * steps, with the source rows in the order the gather lanes consume them, and is shared by every convolution
+ * that uses the kernel map.  Extras: weight_kmajor != 0 - `weight` already is this pass's K-major operand
+ * [K][c_res][c_red] (b2s_weight_to_kmajor output for the forward pass; the input gradient's is the parameter
+ * layout itself), so no per-call transpose and no workspace; bn_sums (fp64 [2][c_res], caller-zeroed) receives
+ * += per-channel sum and sum of squares of the fp16 rows written (batch-norm statistics from the epilogue).
+ * With step_rows == NULL it behaves exactly like b2s_conv_gather_gemm.
+ * b2s_conv_steps_supported: whether (dtype, sizes) can take a step table; b2s_conv_tile_rows: the tile_rows
+ * (128 or 256) the kernel wants for this result width - the table must be built with it.              */
+int32_t b2s_conv_steps_supported(int32_t dtype, int64_t n_src, int32_t c_red, int32_t c_res);
+int32_t b2s_conv_tile_rows(int32_t c_res, int64_t n_rows);
+int b2s_weight_to_kmajor(const void* weight_f16, int32_t k, int32_t c_in, int32_t c_out, void* out_f16,
+                         b2s_stream_t stream);
+int b2s_conv_gather_gemm_steps(int32_t dtype, const void* in, int64_t n_src, const void* weight,
+                               int32_t weight_kmajor, int32_t k, int32_t c_in, int32_t c_out,
+                               int32_t transpose_w, int32_t flip_k, const int32_t* nbr,
+                               const uint32_t* tile_mask, const int32_t* step_rows,
+                               const int32_t* step_start, int32_t tile_rows, const int32_t* row_perm,
+                               int64_t n_rows, const void* bias, void* out, double* bn_sums, void* ws,
+                               size_t ws_bytes, b2s_stream_t stream);
 int b2s_conv_wgrad(int32_t dtype, const void* in, int64_t n_in, const void* grad_out,
                    int64_t n_out, int32_t k, int32_t c_in, int32_t c_out, const int32_t* nbmaps,
                    const int32_t* nbsizes, int32_t swap_pairs, float* grad_w, void* ws,
@@ -208,6 +246,13 @@ int b2s_bn_forward(int32_t dtype, const void* x, const void* residual, int64_t n
                    const float* gamma, const float* beta, float eps, float momentum,
                    float* running_mean, float* running_var, int32_t relu, void* y, float* mean,
                    float* invstd, float* scale_shift, double* sums, b2s_stream_t stream);
+/* b2s_bn_forward with sums_ready != 0: `sums` already holds the per-channel sum / sum of squares of x (the
+ * bn_sums output of b2s_conv_gather_gemm_steps) - the statistics pass over [n, c] is skipped.          */
+int b2s_bn_forward_sums(int32_t dtype, const void* x, const void* residual, int64_t n, int32_t c,
+                        const float* gamma, const float* beta, float eps, float momentum,
+                        float* running_mean, float* running_var, int32_t relu, void* y, float* mean,
+                        float* invstd, float* scale_shift, double* sums, int32_t sums_ready,
+                        b2s_stream_t stream);
 int b2s_bn_backward(int32_t dtype, const void* dy, const void* y, const void* x, int64_t n, int32_t c,
                     const float* mean, const float* invstd, const float* gamma, int32_t relu, void* dx,
                     void* dres, double* sums, b2s_stream_t stream);

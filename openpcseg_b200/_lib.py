@@ -38,6 +38,14 @@ _SIGNATURES = {
     "b2s_conv_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int32, c_int32, c_int32]),
     "b2s_conv_gather_gemm": (c_int32, [c_int32, _P, c_int64, _P, c_int32, c_int32, c_int32, c_int32,
                                        c_int32, _P, _P, _P, c_int64, _P, _P, _P, c_size_t, _P]),
+    "b2s_conv_steps_supported": (c_int32, [c_int32, c_int64, c_int32, c_int32]),
+    "b2s_conv_tile_rows": (c_int32, [c_int32, c_int64]),
+    "b2s_weight_to_kmajor": (c_int32, [_P, c_int32, c_int32, c_int32, _P, _P]),
+    "b2s_conv_gather_gemm_steps": (c_int32, [c_int32, _P, c_int64, _P, c_int32, c_int32, c_int32, c_int32,
+                                             c_int32, c_int32, _P, _P, _P, _P, c_int32, _P, c_int64, _P, _P, _P,
+                                             _P, c_size_t, _P]),
+    "b2s_tile_order_key_bits": (c_int32, [_P, c_int32, c_int64, _P, _P, c_int32, _P, _P, _P]),
+    "b2s_tile_steps": (c_int32, [_P, c_int32, c_int64, _P, _P, c_int32, _P, _P, _P, _P]),
     "b2s_tile_mask": (c_int32, [_P, c_int32, c_int64, _P, _P]),
     "b2s_tile_order_key": (c_int32, [_P, c_int32, c_int64, _P, _P, c_int32, _P, _P]),
     "b2s_conv_wgrad": (c_int32, [c_int32, _P, c_int64, _P, c_int64, c_int32, c_int32, c_int32, _P, _P,
@@ -52,6 +60,8 @@ _SIGNATURES = {
     "b2s_bn_supported": (c_int32, [c_int32, c_int32]),
     "b2s_bn_forward": (c_int32, [c_int32, _P, _P, c_int64, c_int32, _P, _P, c_float, c_float, _P, _P,
                                  c_int32, _P, _P, _P, _P, _P, _P]),
+    "b2s_bn_forward_sums": (c_int32, [c_int32, _P, _P, c_int64, c_int32, _P, _P, c_float, c_float, _P, _P,
+                                      c_int32, _P, _P, _P, _P, _P, c_int32, _P]),
     "b2s_bn_backward": (c_int32, [c_int32, _P, _P, _P, c_int64, c_int32, _P, _P, _P, c_int32, _P, _P, _P,
                                   _P]),
     "b2s_map_count": (c_int32, [_P, c_int64, c_int32, c_int32, c_int32, _P, _P]),

@@ -238,14 +238,53 @@ def tile_mask(nbr: torch.Tensor) -> torch.Tensor:
     return mask
 
 
-def tile_order_key(nbr: torch.Tensor, nbsizes: torch.Tensor, coords: torch.Tensor, coord_shift: int) -> torch.Tensor:
-    """int64 [n] sort keys grouping rows by neighbourhood pattern (b2s_tile_order_key)."""
+def tile_order_key(nbr: torch.Tensor, nbsizes: torch.Tensor, coords: torch.Tensor, coord_shift: int):
+    """(int64 [n] sort keys grouping rows by neighbourhood pattern, uint32-as-int32 [n] presence bits per row)
+    (b2s_tile_order_key_bits)."""
     _cuda(nbr, nbsizes, coords)
     k, n = nbr.shape
     keys = torch.empty(n, dtype=torch.int64, device=nbr.device)
-    check(_lib.lib().b2s_tile_order_key(nbr.data_ptr(), k, n, nbsizes.data_ptr(), coords.contiguous().data_ptr(),
-                                        int(coord_shift), keys.data_ptr(), _stream()), "tile_order_key")
-    return keys
+    bits = torch.empty(n, dtype=torch.int32, device=nbr.device)
+    check(_lib.lib().b2s_tile_order_key_bits(nbr.data_ptr(), k, n, nbsizes.data_ptr(), coords.contiguous().data_ptr(),
+                                             int(coord_shift), keys.data_ptr(), bits.data_ptr(), _stream()),
+          "tile_order_key")
+    return keys, bits
+
+
+def tile_steps(nbr: torch.Tensor, perm: Optional[torch.Tensor], row_bits: Optional[torch.Tensor], tile_rows: int):
+    """Step table of a gather map [K, n] for the tensor-core conv kernel (b2s_tile_steps):
+    (tile_mask int32 [tiles, words], step_start int32 [tiles + 1], step_rows int32 [K * tiles * tile_rows],
+    tile_rows).  Device-resident; step_rows is allocated at its upper bound (same size as the map)."""
+    _cuda(nbr, perm, row_bits)
+    assert nbr.dtype == torch.int32 and nbr.is_contiguous()
+    k, n = nbr.shape
+    tiles = max((n + tile_rows - 1) // tile_rows, 1)
+    dev = nbr.device
+    mask = torch.empty((tiles, (k + 31) // 32), dtype=torch.int32, device=dev)
+    start = torch.empty(tiles + 1, dtype=torch.int32, device=dev)
+    rows = torch.empty(k * tiles * tile_rows, dtype=torch.int32, device=dev)
+    check(_lib.lib().b2s_tile_steps(nbr.data_ptr(), k, n, _ptr(perm), _ptr(row_bits), int(tile_rows), mask.data_ptr(),
+                                    start.data_ptr(), rows.data_ptr(), _stream()), "tile_steps", launches=3)
+    return mask, start, rows, int(tile_rows)
+
+
+def conv_steps_supported(feats: torch.Tensor, c_red: int, c_res: int) -> bool:
+    return feats.dtype == torch.float16 and bool(
+        _lib.lib().b2s_conv_steps_supported(F16, feats.shape[0], int(c_red), int(c_res)))
+
+
+def conv_tile_rows(c_res: int, n_rows: int) -> int:
+    return int(_lib.lib().b2s_conv_tile_rows(int(c_res), int(n_rows)))
+
+
+def weight_to_kmajor(w: torch.Tensor) -> torch.Tensor:
+    """fp16 [K, C_in, C_out] -> [K, C_out, C_in]: the forward pass's K-major operand (b2s_weight_to_kmajor)."""
+    _cuda(w)
+    assert w.dtype == torch.float16 and w.ndim == 3 and w.is_contiguous()
+    k, c_in, c_out = w.shape
+    out = torch.empty((k, c_out, c_in), dtype=torch.float16, device=w.device)
+    check(_lib.lib().b2s_weight_to_kmajor(w.data_ptr(), k, c_in, c_out, out.data_ptr(), _stream()), "weight_to_kmajor")
+    return out
 
 
 def kmap_pairs(nbr_out: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -268,8 +307,14 @@ def conv_gather_gemm(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[to
                      n_rows: int, transpose_w: bool, flip_k: bool,
                      bias: Optional[torch.Tensor] = None, pairs_hint=None,
                      tile_mask: Optional[torch.Tensor] = None,
-                     row_perm: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[r] = sum_k feats[nbr[k'][r]] @ (W[k] or W[k]^T); see b2s_conv_gather_gemm."""
+                     row_perm: Optional[torch.Tensor] = None, steps=None,
+                     weight_kmajor: Optional[torch.Tensor] = None,
+                     bn_sums: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[r] = sum_k feats[nbr[k'][r]] @ (W[k] or W[k]^T); see b2s_conv_gather_gemm(_steps).
+
+    ``steps`` = (tile_mask, step_start, step_rows, tile_rows) of ``tile_steps`` replaces ``nbr`` on the fp16
+    tensor-core path; ``weight_kmajor`` = the cached ``weight_to_kmajor(weight)`` (forward only);
+    ``bn_sums`` fp64 [2, c_res] (zeroed) receives per-channel sum / sum of squares of the result rows."""
     _cuda(feats, weight, nbr, bias)
     feats, weight = feats.contiguous(), weight.contiguous()
     if weight.ndim == 2:
@@ -289,14 +334,25 @@ def conv_gather_gemm(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[to
         return out
     L = _lib.lib()
     code = _dtype_code(feats)
-    nbytes = L.b2s_conv_workspace_bytes(code, n_rows, c_in, c_out, k)
+    w_arg, kmajor = weight, 0
+    if transpose_w:
+        kmajor = 1                       # the parameter layout [K][c_in][c_out] is this pass's K-major operand
+    elif weight_kmajor is not None:
+        w_arg, kmajor = weight_kmajor, 1
+    nbytes = 0 if kmajor else L.b2s_conv_workspace_bytes(code, n_rows, c_in, c_out, k)
     ws = _ws(nbytes, feats.device) if nbytes else None
+    s_mask = s_start = s_rows = None
+    tile_rows = 0
+    if steps is not None:
+        s_mask, s_start, s_rows, tile_rows = steps
+        tile_mask = s_mask
     with _Timed("dgrad" if transpose_w else "fwd",
                 {"k": k, "c_in": c_in, "c_out": c_out, "rows": n_rows, "dtype": code, "pairs": pairs_hint}):
-        check(L.b2s_conv_gather_gemm(code, feats.data_ptr(), feats.shape[0], weight.data_ptr(), k, c_in,
-                                     c_out, int(transpose_w), int(flip_k), _ptr(nbr), _ptr(tile_mask),
-                                     _ptr(row_perm), n_rows, _ptr(bias), out.data_ptr(), _ptr(ws), nbytes,
-                                     _stream()), "conv_gather_gemm")
+        check(L.b2s_conv_gather_gemm_steps(code, feats.data_ptr(), feats.shape[0], w_arg.data_ptr(), kmajor, k, c_in,
+                                           c_out, int(transpose_w), int(flip_k), _ptr(nbr), _ptr(tile_mask),
+                                           _ptr(s_rows), _ptr(s_start), tile_rows, _ptr(row_perm), n_rows,
+                                           _ptr(bias), out.data_ptr(), _ptr(bn_sums), _ptr(ws), nbytes, _stream()),
+              "conv_gather_gemm", launches=1 if kmajor or code != F16 else 2)
     return out
 
 
@@ -424,8 +480,9 @@ def bn_supported(x: torch.Tensor) -> bool:
 
 
 def bn_forward(x: torch.Tensor, residual: Optional[torch.Tensor], gamma, beta, running_mean, running_var,
-               eps: float, momentum: float, relu: bool):
-    """y = act(bn_train(x) [+ residual]); returns (y, mean, invstd)."""
+               eps: float, momentum: float, relu: bool, sums: Optional[torch.Tensor] = None):
+    """y = act(bn_train(x) [+ residual]); returns (y, mean, invstd).  ``sums`` fp64 [2, c]: per-channel sum and
+    sum of squares of x already accumulated by the producing conv (conv_gather_gemm(bn_sums=...))."""
     _cuda(x, residual, gamma, beta, running_mean, running_var)
     x = x.contiguous()
     if residual is not None:
@@ -434,12 +491,15 @@ def bn_forward(x: torch.Tensor, residual: Optional[torch.Tensor], gamma, beta, r
     n, c = x.shape
     y = torch.empty_like(x)
     stat = torch.empty((4, c), dtype=torch.float32, device=x.device)     # mean, invstd, scale, shift
-    sums = torch.empty((2, c), dtype=torch.float64, device=x.device)
-    check(_lib.lib().b2s_bn_forward(_dtype_code(x), x.data_ptr(), _ptr(residual), n, c, _ptr(gamma),
-                                    _ptr(beta), float(eps), float(momentum), _ptr(running_mean),
-                                    _ptr(running_var), int(relu), y.data_ptr(), stat[0].data_ptr(),
-                                    stat[1].data_ptr(), stat[2].data_ptr(), sums.data_ptr(), _stream()),
-          "bn_forward", launches=3)
+    ready = sums is not None
+    if not ready:
+        sums = torch.empty((2, c), dtype=torch.float64, device=x.device)
+    check(_lib.lib().b2s_bn_forward_sums(_dtype_code(x), x.data_ptr(), _ptr(residual), n, c, _ptr(gamma),
+                                         _ptr(beta), float(eps), float(momentum), _ptr(running_mean),
+                                         _ptr(running_var), int(relu), y.data_ptr(), stat[0].data_ptr(),
+                                         stat[1].data_ptr(), stat[2].data_ptr(), sums.data_ptr(), int(ready),
+                                         _stream()),
+          "bn_forward", launches=2 if ready else 3)
     return y, stat[0], stat[1]
 
 

@@ -278,19 +278,30 @@ int b2s_bn_forward(int32_t dtype, const void* x, const void* residual, int64_t n
                    float* running_mean, float* running_var, int32_t relu, void* y, float* mean,
                    float* invstd, float* scale_shift /*[2][c]*/, double* sums /*[2][c]*/,
                    b2s_stream_t stream) {
+  return b2s_bn_forward_sums(dtype, x, residual, n, c, gamma, beta, eps, momentum, running_mean, running_var,
+                             relu, y, mean, invstd, scale_shift, sums, 0, stream);
+}
+
+int b2s_bn_forward_sums(int32_t dtype, const void* x, const void* residual, int64_t n, int32_t c,
+                        const float* gamma, const float* beta, float eps, float momentum,
+                        float* running_mean, float* running_var, int32_t relu, void* y, float* mean,
+                        float* invstd, float* scale_shift /*[2][c]*/, double* sums /*[2][c]*/,
+                        int32_t sums_ready, b2s_stream_t stream) {
   B2S_REQUIRE(dtype == B2S_F32 || dtype == B2S_F16, B2S_ERR_INVALID, "b2s_bn_forward: dtype");
   B2S_REQUIRE(n >= 1 && c >= 1 && x && y && mean && invstd && scale_shift && sums, B2S_ERR_INVALID,
               "b2s_bn_forward: bad argument");
   B2S_REQUIRE(bn_shape_ok(dtype, c), B2S_ERR_UNSUPPORTED, "b2s_bn_forward: C=%d not a vector multiple", c);
   cudaStream_t st = as_stream(stream);
-  cudaMemsetAsync(sums, 0, 2 * c * sizeof(double), st);
   const int w = dtype == B2S_F16 ? 8 : 4;
   const int grid = bn_grid(n, c, w);
   const size_t sh = 2 * c * sizeof(float);
-  if (dtype == B2S_F16)
-    bn_stats_kernel<__half><<<grid, kBnThreads, sh, st>>>(reinterpret_cast<const __half*>(x), n, c, sums);
-  else
-    bn_stats_kernel<float><<<grid, kBnThreads, sh, st>>>(reinterpret_cast<const float*>(x), n, c, sums);
+  if (!sums_ready) {                     // else: accumulated by the producing conv's epilogue (bn_sums)
+    cudaMemsetAsync(sums, 0, 2 * c * sizeof(double), st);
+    if (dtype == B2S_F16)
+      bn_stats_kernel<__half><<<grid, kBnThreads, sh, st>>>(reinterpret_cast<const __half*>(x), n, c, sums);
+    else
+      bn_stats_kernel<float><<<grid, kBnThreads, sh, st>>>(reinterpret_cast<const float*>(x), n, c, sums);
+  }
   bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(sums, n, c, gamma, beta, eps, momentum, running_mean,
                                                       running_var, mean, invstd, scale_shift,
                                                       scale_shift + c);

@@ -16,11 +16,14 @@ int launch_wgrad_simt(const void* in, const void* gout, const int32_t* nbmaps,
 
 // conv_tc.cu
 bool tc_gather_gemm_supported(int c_red, int c_res);
-int launch_gather_gemm_tc(const void* in, int64_t n_src, const void* weight, int k, int c_in, int c_out,
-                          int transpose_w, int flip_k, const int32_t* nbr, const uint32_t* tile_mask,
-                          const int32_t* row_perm, int64_t n_rows, const void* bias, void* out, void* ws,
-                          size_t ws_bytes, cudaStream_t st);
+int launch_gather_gemm_tc(const void* in, int64_t n_src, const void* weight, int weight_kmajor, int k, int c_in,
+                          int c_out, int transpose_w, int flip_k, const int32_t* nbr, const uint32_t* tile_mask,
+                          const int32_t* step_rows, const int32_t* step_start, int tile_rows,
+                          const int32_t* row_perm, int64_t n_rows, const void* bias, void* out, double* bn_sums,
+                          void* ws, size_t ws_bytes, cudaStream_t st);
 size_t tc_gather_gemm_workspace(int k, int c_in, int c_out);
+void launch_weight_to_kmajor(const void* w, int k, int c_in, int c_out, void* out, cudaStream_t st);
+int tc4_tile_rows(int c_res, int64_t n_rows);
 bool tc_wgrad_supported(int c_in, int c_out);
 int launch_wgrad_tc(const void* in, int64_t n_in, const void* gout, int64_t n_out, const int32_t* nbmaps,
                     const int32_t* nbsizes, int64_t n_identity, int64_t n_pairs_bound, int k,
@@ -47,19 +50,46 @@ size_t b2s_conv_workspace_bytes(int32_t dtype, int64_t n_rows, int32_t c_in, int
   return tc_gather_gemm_workspace(k, c_in, c_out);
 }
 
+int32_t b2s_conv_steps_supported(int32_t dtype, int64_t n_src, int32_t c_red, int32_t c_res) {
+  return dtype == B2S_F16 && !force_simt() && tc_gather_gemm_supported(c_red, c_res) &&
+         n_src * (int64_t)c_red * 2 < (int64_t)0xFFFFFF00LL;
+}
+
+int32_t b2s_conv_tile_rows(int32_t c_res, int64_t n_rows) { return tc4_tile_rows(c_res, n_rows); }
+
+int b2s_weight_to_kmajor(const void* weight, int32_t k, int32_t c_in, int32_t c_out, void* out,
+                         b2s_stream_t stream) {
+  B2S_REQUIRE(weight && out && k >= 1 && c_in >= 1 && c_out >= 1, B2S_ERR_INVALID, "b2s_weight_to_kmajor: bad argument");
+  launch_weight_to_kmajor(weight, k, c_in, c_out, out, as_stream(stream));
+  B2S_CHECK_LAUNCH("b2s_weight_to_kmajor");
+  return B2S_OK;
+}
+
 int b2s_conv_gather_gemm(int32_t dtype, const void* in, int64_t n_src, const void* weight,
                          int32_t k, int32_t c_in, int32_t c_out, int32_t transpose_w,
                          int32_t flip_k, const int32_t* nbr, const uint32_t* tile_mask,
                          const int32_t* row_perm, int64_t n_rows, const void* bias, void* out, void* ws,
                          size_t ws_bytes, b2s_stream_t stream) {
+  return b2s_conv_gather_gemm_steps(dtype, in, n_src, weight, 0, k, c_in, c_out, transpose_w, flip_k, nbr,
+                                    tile_mask, nullptr, nullptr, 0, row_perm, n_rows, bias, out, nullptr, ws,
+                                    ws_bytes, stream);
+}
+
+int b2s_conv_gather_gemm_steps(int32_t dtype, const void* in, int64_t n_src, const void* weight,
+                               int32_t weight_kmajor, int32_t k, int32_t c_in, int32_t c_out,
+                               int32_t transpose_w, int32_t flip_k, const int32_t* nbr,
+                               const uint32_t* tile_mask, const int32_t* step_rows,
+                               const int32_t* step_start, int32_t tile_rows, const int32_t* row_perm,
+                               int64_t n_rows, const void* bias, void* out, double* bn_sums, void* ws,
+                               size_t ws_bytes, b2s_stream_t stream) {
   B2S_REQUIRE(dtype == B2S_F32 || dtype == B2S_F16, B2S_ERR_INVALID, "b2s_conv_gather_gemm: dtype");
   B2S_REQUIRE(k >= 1 && c_in >= 1 && c_out >= 1 && n_rows >= 0 && n_src >= 0, B2S_ERR_INVALID,
               "b2s_conv_gather_gemm: bad sizes");
   if (n_rows == 0) return B2S_OK;
-  B2S_REQUIRE(nbr || k == 1, B2S_ERR_INVALID,
+  B2S_REQUIRE(nbr || step_rows || k == 1, B2S_ERR_INVALID,
               "b2s_conv_gather_gemm: nbr == NULL (identity map) needs k == 1");
-  B2S_REQUIRE(nbr || !row_perm, B2S_ERR_INVALID, "b2s_conv_gather_gemm: row_perm needs a gather map");
-  B2S_REQUIRE(nbr || n_rows <= n_src, B2S_ERR_INVALID,
+  B2S_REQUIRE(nbr || step_rows || !row_perm, B2S_ERR_INVALID, "b2s_conv_gather_gemm: row_perm needs a gather map");
+  B2S_REQUIRE(nbr || step_rows || n_rows <= n_src, B2S_ERR_INVALID,
               "b2s_conv_gather_gemm: identity map with n_rows > n_src");
   B2S_REQUIRE(in && weight && out, B2S_ERR_INVALID, "b2s_conv_gather_gemm: null pointer");
   B2S_REQUIRE(n_rows < (1LL << 31) && n_src < (1LL << 31), B2S_ERR_UNSUPPORTED,
@@ -69,10 +99,18 @@ int b2s_conv_gather_gemm(int32_t dtype, const void* in, int64_t n_src, const voi
   const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(weight) |
                          reinterpret_cast<uintptr_t>(out)) & 15) == 0;
   if (dtype == B2S_F16 && !force_simt() && aligned && tc_gather_gemm_supported(c_red, c_res)) {
-    int rc = launch_gather_gemm_tc(in, n_src, weight, k, c_in, c_out, transpose_w, flip_k, nbr, tile_mask,
-                                   row_perm, n_rows, bias, out, ws, ws_bytes, st);
+    int rc = launch_gather_gemm_tc(in, n_src, weight, weight_kmajor, k, c_in, c_out, transpose_w, flip_k, nbr,
+                                   tile_mask, step_rows, step_start, tile_rows, row_perm, n_rows, bias, out,
+                                   bn_sums, ws, ws_bytes, st);
     if (rc != B2S_OK) return rc;
-  } else if (dtype == B2S_F16) {
+    B2S_CHECK_LAUNCH("b2s_conv_gather_gemm");
+    return B2S_OK;
+  }
+  // (for the input gradient the "K-major" operand IS the parameter layout the CUDA-core kernels read)
+  B2S_REQUIRE(!step_rows && !bn_sums && (!weight_kmajor || transpose_w), B2S_ERR_UNSUPPORTED,
+              "b2s_conv_gather_gemm: step tables / bn_sums / K-major weights need the tensor-core kernels "
+              "(check b2s_conv_steps_supported)");
+  if (dtype == B2S_F16) {
     launch_gather_gemm_simt<__half>(in, weight, k, c_in, c_out, transpose_w, flip_k, nbr, row_perm,
                                     n_rows, bias, out, st);
   } else {

@@ -1,21 +1,11 @@
-// Sparse convolution, tensor-core kernel family (fp16 in, fp32 accumulate) for sm_100a:
-// tcgen05.mma with the accumulator in TMEM, operands staged in 128B/64B-swizzled shared
-// memory by cp.async (LDGSTS, 16-byte row segments, zero-fill for missing neighbours),
-// mbarrier producer/consumer pipeline, warp-specialised:
+// Sparse convolution, tensor-core kernel family (fp16 in, fp32 accumulate) for sm_100a: dispatch of the
+// forward / input-gradient gather-GEMM (conv_tc4.cu step-table kernel; conv_tc2.cu for maps without a step
+// table and for inputs of 4 GiB and more) and the weight-gradient kernel (below).
 //
-//   warps 0-3  producers: gather the 128 neighbour rows of offset k (A tile) and the
-//              weight slice W_k^T (B tile) into the stage ring; afterwards the same
-//              four warps are the epilogue (TMEM -> registers -> fp16 -> global rows)
-//   warp  4    allocates TMEM, one elected lane issues tcgen05.mma / tcgen05.commit
-//
-// Output-stationary implicit GEMM: one CTA owns 128 output rows and accumulates ALL kernel
-// offsets (k-loop x channel chunks) into one TMEM accumulator [128 lanes x C_res columns];
-// offsets for which no row of the tile has a neighbour are skipped.  One write per output
-// row, fp32 accumulation across offsets, no atomics, deterministic.
-//
-// Roofline: tensor pipe for C >= 128 layers; L2->SM gather bandwidth / LDGSTS
-// issue for narrow layers.  Algorithmic FLOPs = 2 * M * C_in * C_out (M = map pairs);
-// algorithmic bytes = 2*C_red*M (gathered rows) + 2*C_res*N_rows + 4*K*N_rows + 2*K*C_in*C_out.
+// Output-stationary implicit GEMM: one CTA tile owns 128 (or 256) output rows and accumulates ALL kernel
+// offsets into one TMEM accumulator; one write per output row, fp32 accumulation across offsets, no atomics.
+// Algorithmic FLOPs = 2 * M * C_in * C_out (M = map pairs); algorithmic bytes = 2*C_red*M (gathered rows) +
+// 2*C_res*N_rows + 4*K*N_rows + 2*K*C_in*C_out.
 #include <stdlib.h>
 
 #include <cuda.h>
@@ -26,187 +16,6 @@
 namespace b2s {
 
 namespace tc {
-
-struct Params {
-  const __half* in;     // [n_src, c_red]
-  const __half* wt;     // [K][c_res][c_red]  (K-major B operand)
-  const int32_t* nbr;   // [K][n_rows] or nullptr (identity, K == 1)
-  const int32_t* row_perm;  // out row of launch row j, or nullptr
-  const __half* bias;   // [c_res] or nullptr
-  __half* out;          // [n_rows, c_res]
-  int64_t n_rows;
-  int kvol, c_red, c_res, flip_k;
-  int stages, tmem_cols;
-};
-
-// BK = channels per stage (64 -> 128-byte rows, 32 -> 64-byte rows)
-template <int BK>
-__global__ void __launch_bounds__(kThreads) gather_gemm_tc_kernel(const Params p) {
-  constexpr int ROWB = BK * 2;
-  constexpr int CH = ROWB / 16;          // 16-byte chunks per row
-  constexpr int RPI = 32 / CH;           // rows covered by one warp-wide cp.async
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // dynamic smem is only 16-byte aligned by contract: align the tile ring to 1024 by hand
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const int a_bytes = kTileM * ROWB;
-  const int b_bytes = ((p.c_res + 7) / 8) * 8 * ROWB;
-  const int stage_bytes = a_bytes + b_bytes;                 // multiple of 512; keep 1024-aligned
-  const int stage_stride = (stage_bytes + 1023) & ~1023;
-  __shared__ __align__(8) uint64_t s_full[8];
-  __shared__ __align__(8) uint64_t s_empty[8];
-  __shared__ __align__(8) uint64_t s_acc;
-  __shared__ uint32_t s_tmem;
-  __shared__ uint32_t s_active[8];       // bit k set <=> some row of the tile has neighbour k
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t row0 = (int64_t)blockIdx.x * kTileM;
-  const int S = p.stages;
-
-  if (tid < 8) s_active[tid] = 0;
-  if (tid == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(smem_u32(&s_full[s]), kProducerThreads);
-      mbar_init(smem_u32(&s_empty[s]), 1);
-    }
-    mbar_init(smem_u32(&s_acc), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 4) tmem_alloc(smem_u32(&s_tmem), (uint32_t)p.tmem_cols);
-  __syncthreads();
-  // which offsets does this tile need at all?
-  if (warp < 4) {
-    const int64_t r = row0 + tid;
-    for (int k = 0; k < p.kvol; ++k) {
-      bool have = false;
-      if (r < p.n_rows)
-        have = p.nbr ? (__ldg(p.nbr + (int64_t)(p.flip_k ? p.kvol - 1 - k : k) * p.n_rows + r) >= 0)
-                     : true;
-      unsigned m = __ballot_sync(0xffffffffu, have);
-      if (lane == 0 && m) atomicOr(&s_active[k >> 5], 1u << (k & 31));
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_acc = s_tmem;
-  const int chunks = p.c_red / BK;
-  int n_active = 0;
-  for (int w = 0; w < 8; ++w) n_active += __popc(s_active[w]);
-  const int iters = n_active * chunks;
-
-  if (warp < 4) {
-    // ------------------------------------------------------------------ producers
-    const int LAG = S >= 3 ? 2 : 1;       // stages in flight before the full-barrier arrive (<= S-1)
-    const int sub = lane / CH, chunk = lane % CH;
-    int it = 0;
-    for (int k = 0; k < p.kvol; ++k) {
-      if (!((s_active[k >> 5] >> (k & 31)) & 1u)) continue;
-      // neighbour row of (this warp's row `lane`) for offset k
-      int32_t my_src = -1;
-      {
-        const int64_t r = row0 + warp * 32 + lane;
-        if (r < p.n_rows)
-          my_src = p.nbr ? __ldg(p.nbr + (int64_t)(p.flip_k ? p.kvol - 1 - k : k) * p.n_rows + r)
-                         : (int32_t)r;
-      }
-      const __half* wk = p.wt + (int64_t)k * p.c_res * p.c_red;
-      for (int c = 0; c < chunks; ++c, ++it) {
-        const int s = it % S;
-        if (it >= S) mbar_wait(smem_u32(&s_empty[s]), ((it / S) - 1) & 1);
-        const uint32_t a_base = smem_base + s * stage_stride;
-        const uint32_t b_base = a_base + a_bytes;
-        const int ch0 = c * BK + chunk * 8;
-        // A: 32 rows per warp, RPI rows per instruction
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {
-          const int rl = i * RPI + sub;                       // row within this warp's 32
-          const int32_t src = __shfl_sync(0xffffffffu, my_src, rl);
-          const __half* g = src >= 0 ? p.in + (int64_t)src * p.c_red + ch0 : p.in;
-          cp_async16(a_base + swz<ROWB>(warp * 32 + rl, chunk), g, src >= 0 ? 16u : 0u);
-        }
-        // B: c_res rows of W_k^T, spread over the 128 producer threads
-        for (int n = warp * RPI + sub; n < p.c_res; n += 4 * RPI)
-          cp_async16(b_base + swz<ROWB>(n, chunk), wk + (int64_t)n * p.c_red + ch0, 16u);
-        cp_async_commit();
-        if (it >= LAG) {
-          if (LAG == 2) cp_async_wait<2>();
-          else cp_async_wait<1>();
-          fence_proxy_async();
-          mbar_arrive(smem_u32(&s_full[(it - LAG) % S]));
-        }
-      }
-    }
-    // drain: signal the last min(LAG, iters) stages
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int j = (iters > LAG ? iters - LAG : 0); j < iters; ++j) mbar_arrive(smem_u32(&s_full[j % S]));
-
-    // -------------------------------------------------------------------- epilogue
-    if (iters > 0) {
-      mbar_wait(smem_u32(&s_acc), 0);
-      tc_fence_after();
-    }
-    const int64_t r = row0 + warp * 32 + lane;
-    const int64_t r_out = (p.row_perm && r < p.n_rows) ? (int64_t)__ldg(p.row_perm + r) : r;
-    const uint32_t t_lane = tmem_acc + ((uint32_t)(warp * 32) << 16);
-    for (int c0 = 0; c0 < p.c_res; c0 += 16) {
-      uint32_t v[16];
-      if (iters > 0) {
-        tmem_ld16(t_lane + (uint32_t)c0, v);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0u;
-      }
-      if (r < p.n_rows) {
-        __align__(16) __half h[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float f = __uint_as_float(v[j]);
-          if (p.bias) f += __half2float(__ldg(p.bias + c0 + j));
-          h[j] = __float2half_rn(f);
-        }
-        uint4* dst = reinterpret_cast<uint4*>(p.out + r_out * p.c_res + c0);
-        dst[0] = reinterpret_cast<const uint4*>(h)[0];
-        dst[1] = reinterpret_cast<const uint4*>(h)[1];
-      }
-    }
-    tc_fence_before();
-  } else {
-    // ------------------------------------------------------------------ MMA issuer
-    const int n_half = p.c_res > 256 ? p.c_res / 2 : p.c_res;
-    const uint32_t idesc = make_idesc(n_half);
-    for (int it = 0; it < iters; ++it) {
-      const int s = it % S;
-      mbar_wait(smem_u32(&s_full[s]), (it / S) & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_base = smem_base + s * stage_stride;
-        const uint32_t b_base = a_base + a_bytes;
-#pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-          const uint64_t ad = make_desc<ROWB>(a_base + kk * 32);
-          const uint64_t bd = make_desc<ROWB>(b_base + kk * 32);
-          umma_f16(tmem_acc, ad, bd, idesc, (it | kk) ? 1u : 0u);
-          if (n_half != p.c_res) {
-            const uint64_t bd2 = make_desc<ROWB>(b_base + (n_half / 8) * (8 * ROWB) + kk * 32);
-            umma_f16(tmem_acc + (uint32_t)n_half, ad, bd2, idesc, (it | kk) ? 1u : 0u);
-          }
-        }
-        umma_commit(smem_u32(&s_empty[s]));       // frees the stage when the MMAs retire
-        if (it == iters - 1) umma_commit(smem_u32(&s_acc));
-      }
-      __syncwarp();
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 4) {
-    tc_fence_after();
-    tmem_dealloc(tmem_acc, (uint32_t)p.tmem_cols);
-  }
-}
-
 // W [K][c_in][c_out] -> W^T [K][c_out][c_in] (the K-major B operand of the forward pass)
 __global__ void __launch_bounds__(256) transpose_weight_kernel(const __half* __restrict__ w,
                                                                 __half* __restrict__ wt, int c_in,
@@ -240,27 +49,10 @@ int launch_gather_gemm_tc2(const void* in, const void* wt, int k, int c_red, int
                            const int32_t* nbr, const uint32_t* tile_mask, const int32_t* row_perm,
                            int64_t n_rows, const void* bias, void* out, cudaStream_t st);
 
-int launch_gather_gemm_tc3(const void* in, int64_t n_src, const void* wt, int k, int c_red, int c_res, int flip_k,
-                           const int32_t* nbr, const uint32_t* tile_mask, const int32_t* row_perm,
-                           int64_t n_rows, const void* bias, void* out, cudaStream_t st);
-
-static bool use_v2() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B2S_TC_V2");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
-static bool use_v1() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B2S_TC_V1");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
+int launch_gather_gemm_tc4(const void* in, int64_t n_src, const void* wt, int k, int c_red, int c_res, int flip_k,
+                           const int32_t* step_rows, const int32_t* step_start, const uint32_t* tile_mask,
+                           int tile_rows, const int32_t* row_perm, int64_t n_rows, const void* bias, void* out,
+                           double* bn_sums, cudaStream_t st);
 
 bool tc_gather_gemm_supported(int c_red, int c_res) {
   if (c_red % 32 != 0 || c_red < 32) return false;
@@ -273,64 +65,41 @@ size_t tc_gather_gemm_workspace(int k, int c_in, int c_out) {
   return align_up((size_t)k * c_in * c_out * sizeof(__half), 256);   // W^T for the forward pass
 }
 
-int launch_gather_gemm_tc(const void* in, int64_t n_src, const void* weight, int k, int c_in, int c_out,
-                          int transpose_w, int flip_k, const int32_t* nbr, const uint32_t* tile_mask,
-                          const int32_t* row_perm, int64_t n_rows, const void* bias, void* out, void* ws,
-                          size_t ws_bytes, cudaStream_t st) {
+// fp16 W [K][c_in][c_out] -> the K-major B operand of the forward pass [K][c_out][c_in]
+void launch_weight_to_kmajor(const void* w, int k, int c_in, int c_out, void* out, cudaStream_t st) {
+  dim3 g((unsigned)ceil_div(c_out, 32), (unsigned)ceil_div(c_in, 32), (unsigned)k);
+  tc::transpose_weight_kernel<<<g, 256, 0, st>>>(reinterpret_cast<const __half*>(w), reinterpret_cast<__half*>(out),
+                                                 c_in, c_out);
+}
+
+// weight_kmajor != 0: `weight` already is the K-major B operand of this pass ([K][c_res][c_red]); otherwise it is
+// the parameter layout [K][c_in][c_out], which the input gradient consumes as is and the forward pass transposes
+// into the workspace.  steps != nullptr selects the step-table kernel.
+int launch_gather_gemm_tc(const void* in, int64_t n_src, const void* weight, int weight_kmajor, int k, int c_in,
+                          int c_out, int transpose_w, int flip_k, const int32_t* nbr, const uint32_t* tile_mask,
+                          const int32_t* step_rows, const int32_t* step_start, int tile_rows,
+                          const int32_t* row_perm, int64_t n_rows, const void* bias, void* out, double* bn_sums,
+                          void* ws, size_t ws_bytes, cudaStream_t st) {
   using namespace tc;
   const int c_red = transpose_w ? c_out : c_in, c_res = transpose_w ? c_in : c_out;
   const __half* wt = reinterpret_cast<const __half*>(weight);
-  if (!transpose_w) {
+  if (!transpose_w && !weight_kmajor) {
     // forward: B_k[n = c_out][c = c_in] = W[k][c][n]  -> needs W^T
     B2S_REQUIRE(ws && ws_bytes >= tc_gather_gemm_workspace(k, c_in, c_out), B2S_ERR_WORKSPACE,
                 "b2s_conv_gather_gemm: workspace needs %zu bytes",
                 tc_gather_gemm_workspace(k, c_in, c_out));
-    dim3 g((unsigned)ceil_div(c_out, 32), (unsigned)ceil_div(c_in, 32), (unsigned)k);
-    transpose_weight_kernel<<<g, 256, 0, st>>>(wt, reinterpret_cast<__half*>(ws), c_in, c_out);
+    launch_weight_to_kmajor(weight, k, c_in, c_out, ws, st);
     wt = reinterpret_cast<const __half*>(ws);
   }  // input gradient: B_k[n = c_in][c = c_out] = W[k][n][c] is the stored layout already
-  // persistent kernel: needs the tile masks, and addresses source rows by 32-bit byte offsets
-  const bool small_src = n_src * (int64_t)c_red * 2 < (int64_t)0xFFFFFF00LL;
-  if (!use_v1() && !use_v2() && nbr && tile_mask && small_src)
-    return launch_gather_gemm_tc3(in, n_src, wt, k, c_red, c_res, flip_k, nbr, tile_mask, row_perm, n_rows, bias,
-                                  out, st);
-  if (!use_v1())
-    return launch_gather_gemm_tc2(in, wt, k, c_red, c_res, flip_k, nbr, tile_mask, row_perm, n_rows, bias,
-                                  out, st);
-  Params p;
-  p.in = reinterpret_cast<const __half*>(in);
-  p.wt = wt;
-  p.nbr = nbr;
-  p.row_perm = row_perm;
-  p.bias = reinterpret_cast<const __half*>(bias);
-  p.out = reinterpret_cast<__half*>(out);
-  p.n_rows = n_rows;
-  p.kvol = k;
-  p.c_red = c_red;
-  p.c_res = c_res;
-  p.flip_k = flip_k;
-  p.tmem_cols = tmem_cols_for(c_res);
-  const bool bk64 = (c_red % 64 == 0);
-  const int rowb = bk64 ? 128 : 64;
-  const int stage = ((kTileM * rowb + ((c_res + 7) / 8) * 8 * rowb) + 1023) & ~1023;
-  // two CTAs per SM when the ring fits twice (and TMEM allows it), else one deep ring
-  int stages = (110 * 1024) / stage;
-  if (stages < 3 || p.tmem_cols > 256) stages = (220 * 1024) / stage;
-  if (stages > 6) stages = 6;
-  B2S_REQUIRE(stages >= 2, B2S_ERR_UNSUPPORTED, "b2s_conv_gather_gemm: tile does not fit (C=%d)", c_res);
-  p.stages = stages;
-  const size_t smem = (size_t)stages * stage + 1024;
-  const unsigned grid = (unsigned)ceil_div(n_rows, kTileM);
-  if (bk64) {
-    cudaFuncSetAttribute(gather_gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)smem);
-    gather_gemm_tc_kernel<64><<<grid, kThreads, smem, st>>>(p);
-  } else {
-    cudaFuncSetAttribute(gather_gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)smem);
-    gather_gemm_tc_kernel<32><<<grid, kThreads, smem, st>>>(p);
+  if (step_rows) {
+    // the step-table kernel addresses source rows by 32-bit byte offsets (b2s_conv_steps_supported)
+    B2S_REQUIRE(step_start && tile_mask && n_src * (int64_t)c_red * 2 < (int64_t)0xFFFFFF00LL, B2S_ERR_INVALID,
+                "b2s_conv_gather_gemm: step table without masks, or a source tensor of 4 GiB and more");
+    return launch_gather_gemm_tc4(in, n_src, wt, k, c_red, c_res, flip_k, step_rows, step_start, tile_mask,
+                                  tile_rows, row_perm, n_rows, bias, out, bn_sums, st);
   }
-  return B2S_OK;
+  B2S_REQUIRE(!bn_sums, B2S_ERR_UNSUPPORTED, "b2s_conv_gather_gemm: bn_sums needs the step-table kernel");
+  return launch_gather_gemm_tc2(in, wt, k, c_red, c_res, flip_k, nbr, tile_mask, row_perm, n_rows, bias, out, st);
 }
 
 // =====================================================================================
@@ -390,8 +159,8 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tm,
       : "memory");
 }
 
-// kTma = false: rows copied with cp.async.  kTma = true (experimental, B2S_WG_GATHER4=1, not yet run on
-// hardware): the producer warps hand the pair indices to the TMA unit, four rows per tile::gather4
+// kTma = false: rows copied with cp.async.  kTma = true (default for C_out <= 128, B2S_WG_GATHER4 forces):
+// the producer warps hand the pair indices to the TMA unit, four rows per tile::gather4
 // (tmx / tmy describe x and gy as [rows, channels] tensors with a one-row, 64-channel box; channels past
 // the tensor width are zero-filled), and the stage barrier counts bytes instead of thread arrivals.
 template <bool kTma>
@@ -617,7 +386,7 @@ bool tc_wgrad_supported(int c_in, int c_out) {
   return true;                                                 // C_out > 256 splits as 256 + rest
 }
 
-bool tc_make_row_map(CUtensorMap* tm, const void* base, int64_t rows, int cols, int box_cols);   // conv_tc3.cu
+bool tc_make_row_map(CUtensorMap* tm, const void* base, int64_t rows, int cols, int box_cols);   // conv_tc4.cu
 
 namespace tcw {
 template <bool kTma>
@@ -680,11 +449,14 @@ int launch_wgrad_tc(const void* in, int64_t n_in, const void* gout, int64_t n_ou
   int64_t max_units = (n_pairs_bound / unit + k) * p.m_tiles;
   const int64_t slots = (int64_t)sms * (two_per_sm ? 2 : 1);
   int grid = (int)(max_units < slots ? (max_units < 1 ? 1 : max_units) : slots);
-  // experimental: both operands fetched by the TMA unit (tile::gather4), see the kernel
-  static const bool gather4 = [] {
+  // Both operands fetched by the TMA unit (tile::gather4) where it measured faster than cp.async
+  // (profiles/r2_gather4_validation.txt, batch 4: C_out <= 128 layers 3-23 % faster, 256-channel layers
+  // 3-6 % slower: the unit sustains one 4-row gather per ~13 cycles per SM); B2S_WG_GATHER4=0/1 forces.
+  static const int g4_env = [] {
     const char* e = getenv("B2S_WG_GATHER4");
-    return e && e[0] == '1';
+    return e ? (e[0] == '1' ? 1 : 0) : -1;
   }();
+  const bool gather4 = g4_env >= 0 ? g4_env == 1 : (c_out <= 128 && c_in % 8 == 0);
   CUtensorMap tmx, tmy;
   memset(&tmx, 0, sizeof(tmx));
   memset(&tmy, 0, sizeof(tmy));

@@ -216,7 +216,8 @@ __global__ void __launch_bounds__(128) tile_mask_kernel(const int32_t* __restric
 __global__ void __launch_bounds__(256) tile_order_key_kernel(const int32_t* __restrict__ nbr, int kvol,
                                                               int64_t n, const int32_t* __restrict__ nbsizes,
                                                               const int4* __restrict__ coords, int shift,
-                                                              int64_t* __restrict__ keys) {
+                                                              int64_t* __restrict__ keys,
+                                                              uint32_t* __restrict__ row_bits, int batch_major) {
   __shared__ int s_bit[32];
   if (threadIdx.x < kvol) {
     const int mine = nbsizes[threadIdx.x];
@@ -231,12 +232,101 @@ __global__ void __launch_bounds__(256) tile_order_key_kernel(const int32_t* __re
   for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < n;
        r += (int64_t)gridDim.x * blockDim.x) {
     uint64_t m = 0;
+    uint32_t bits = 0;
     for (int k = 0; k < kvol; ++k)
-      if (__ldg(nbr + (int64_t)k * n + r) >= 0) m |= 1ULL << s_bit[k];
+      if (__ldg(nbr + (int64_t)k * n + r) >= 0) {
+        m |= 1ULL << s_bit[k];
+        bits |= 1u << k;
+      }
+    if (row_bits) row_bits[r] = bits;
     const int4 c = __ldg(coords + r);
-    const uint64_t zc = (uint64_t)((c.z >> shift) & 0x3FF), xc = (uint64_t)((c.x >> shift) & 0x1FFF),
-                   yc = (uint64_t)((c.y >> shift) & 0x1FFF);
-    keys[r] = (int64_t)((m << 36) | (zc << 26) | (xc << 13) | yc);
+    if (batch_major) {
+      // [batch 8][pattern 27][z 8][x 10][y 10]: tiles never mix scans, and the static round-robin of tiles over
+      // CTAs keeps ~one scan's rows (18 MB at 96 channels) in flight - they stay in L2 across the ~4.7 offsets
+      // that gather each of them; with the pattern as the leading key a tile mixed all scans of the batch and
+      // every gather of a 16-scan batch (290 MB of rows) went to DRAM
+      const uint64_t zc = (uint64_t)((c.z >> shift) & 0xFF), xc = (uint64_t)((c.x >> (shift + 1)) & 0x3FF),
+                     yc = (uint64_t)((c.y >> (shift + 1)) & 0x3FF);
+      keys[r] = (int64_t)(((uint64_t)(c.w & 0xFF) << 55) | (m << 28) | (zc << 20) | (xc << 10) | yc);
+    } else {
+      const uint64_t zc = (uint64_t)((c.z >> shift) & 0x3FF), xc = (uint64_t)((c.x >> shift) & 0x1FFF),
+                     yc = (uint64_t)((c.y >> shift) & 0x1FFF);
+      keys[r] = (int64_t)((m << 36) | (zc << 26) | (xc << 13) | yc);
+    }
+  }
+}
+
+// ---- step table of a gather map (consumed by conv_tc4.cu) --------------------------------------------
+// pass 1: active-offset mask of every tile of `tile_rows` launch rows + its popcount
+template <int TR>
+__global__ void __launch_bounds__(TR) tile_steps_mask_kernel(const int32_t* __restrict__ nbr, int kvol, int64_t n,
+                                                             const int32_t* __restrict__ perm,
+                                                             const uint32_t* __restrict__ row_bits,
+                                                             uint32_t* __restrict__ mask,
+                                                             int32_t* __restrict__ counts) {
+  __shared__ uint32_t s_m[4];
+  const int words = (kvol + 31) >> 5;
+  if (threadIdx.x < 4) s_m[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t j = (int64_t)blockIdx.x * TR + threadIdx.x;
+  const int64_t r = j < n ? (perm ? (int64_t)__ldg(perm + j) : j) : -1;
+  if (row_bits && kvol <= 32) {
+    const uint32_t b = __reduce_or_sync(0xffffffffu, r >= 0 ? __ldg(row_bits + r) : 0u);
+    if ((threadIdx.x & 31) == 0 && b) atomicOr(&s_m[0], b);
+  } else {
+    for (int k = 0; k < kvol; ++k) {
+      const bool have = r >= 0 && __ldg(nbr + (int64_t)k * n + r) >= 0;
+      const unsigned b = __ballot_sync(0xffffffffu, have);
+      if ((threadIdx.x & 31) == 0 && b) atomicOr(&s_m[k >> 5], 1u << (k & 31));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < words) mask[(int64_t)blockIdx.x * words + threadIdx.x] = s_m[threadIdx.x];
+  if (threadIdx.x == 0) counts[blockIdx.x] = __popc(s_m[0]) + __popc(s_m[1]) + __popc(s_m[2]) + __popc(s_m[3]);
+}
+
+// pass 2: in-place exclusive scan of the per-tile counts (one CTA; a level has at most a few 10^4 tiles)
+__global__ void __launch_bounds__(1024) tile_steps_scan_kernel(int32_t* __restrict__ counts, int n_tiles) {
+  using Scan = cub::BlockScan<int, 1024>;
+  __shared__ typename Scan::TempStorage tmp;
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base <= n_tiles; base += 1024) {          // entry n_tiles receives the total
+    const int i = base + threadIdx.x;
+    const int v = i < n_tiles ? counts[i] : 0;
+    int excl, total;
+    Scan(tmp).ExclusiveSum(v, excl, total);
+    const int carry = s_carry;
+    if (i <= n_tiles) counts[i] = carry + excl;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + total;
+    __syncthreads();
+  }
+}
+
+// pass 3: the source rows of every active (tile, offset) step in the gather lanes' order
+template <int TR>
+__global__ void __launch_bounds__(TR) tile_steps_fill_kernel(const int32_t* __restrict__ nbr, int kvol, int64_t n,
+                                                             const int32_t* __restrict__ perm,
+                                                             const uint32_t* __restrict__ mask,
+                                                             const int32_t* __restrict__ step_start,
+                                                             int32_t* __restrict__ step_rows) {
+  const int words = (kvol + 31) >> 5;
+  const int t = threadIdx.x;
+  const int64_t j = (int64_t)blockIdx.x * TR + t;
+  const int64_t r = j < n ? (perm ? (int64_t)__ldg(perm + j) : j) : -1;
+  // tile row w*32 + i*4 + q  ->  slot w*32 + q*8 + i
+  const int pos = (t & ~31) + (t & 3) * 8 + ((t & 31) >> 2);
+  int64_t s = __ldg(step_start + blockIdx.x);
+  for (int w = 0; w < words; ++w) {
+    uint32_t bits = __ldg(mask + (int64_t)blockIdx.x * words + w);
+    while (bits) {
+      const int k = w * 32 + __ffs(bits) - 1;
+      bits &= bits - 1;
+      step_rows[s * TR + pos] = r >= 0 ? __ldg(nbr + (int64_t)k * n + r) : -1;
+      ++s;
+    }
   }
 }
 
@@ -437,15 +527,54 @@ int b2s_kmap_build(const int32_t* in_coords, int64_t n_in, const int32_t* out_co
   return B2S_OK;
 }
 
-int b2s_tile_order_key(const int32_t* nbr, int32_t k, int64_t n, const int32_t* nbsizes,
-                       const int32_t* coords, int32_t coord_shift, int64_t* keys, b2s_stream_t stream) {
+int b2s_tile_order_key_bits(const int32_t* nbr, int32_t k, int64_t n, const int32_t* nbsizes,
+                            const int32_t* coords, int32_t coord_shift, int64_t* keys, uint32_t* row_bits,
+                            b2s_stream_t stream) {
   B2S_REQUIRE(k >= 1 && k <= 27 && n >= 0 && coord_shift >= 0 && coord_shift < 16, B2S_ERR_INVALID,
               "b2s_tile_order_key: bad sizes (kernel volume must be <= 27)");
   if (n == 0) return B2S_OK;
   B2S_REQUIRE(nbr && nbsizes && coords && keys, B2S_ERR_INVALID, "b2s_tile_order_key: null pointer");
+  static const int batch_major = [] {
+    const char* e = getenv("B2S_TILE_BATCH_MAJOR");
+    return (e && e[0] == '1') ? 1 : 0;        // measured (profiles/r2_tile_order.txt): batch-major loses 7-28 %
+  }();
   tile_order_key_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
-      nbr, k, n, nbsizes, reinterpret_cast<const int4*>(coords), coord_shift, keys);
+      nbr, k, n, nbsizes, reinterpret_cast<const int4*>(coords), coord_shift, keys, row_bits, batch_major);
   B2S_CHECK_LAUNCH("b2s_tile_order_key");
+  return B2S_OK;
+}
+
+int b2s_tile_order_key(const int32_t* nbr, int32_t k, int64_t n, const int32_t* nbsizes,
+                       const int32_t* coords, int32_t coord_shift, int64_t* keys, b2s_stream_t stream) {
+  return b2s_tile_order_key_bits(nbr, k, n, nbsizes, coords, coord_shift, keys, nullptr, stream);
+}
+
+int b2s_tile_steps(const int32_t* nbr, int32_t k, int64_t n, const int32_t* perm, const uint32_t* row_bits,
+                   int32_t tile_rows, uint32_t* tile_mask, int32_t* step_start, int32_t* step_rows,
+                   b2s_stream_t stream) {
+  B2S_REQUIRE(k >= 1 && k <= 128 && n >= 0 && (tile_rows == 128 || tile_rows == 256), B2S_ERR_INVALID,
+              "b2s_tile_steps: bad sizes");
+  B2S_REQUIRE(step_start, B2S_ERR_INVALID, "b2s_tile_steps: null pointer");
+  cudaStream_t st = as_stream(stream);
+  const int64_t tiles = ceil_div(n, (int64_t)tile_rows);
+  B2S_REQUIRE(tiles * k < (1LL << 31), B2S_ERR_UNSUPPORTED, "b2s_tile_steps: too many steps");
+  if (n == 0) {
+    cudaMemsetAsync(step_start, 0, sizeof(int32_t), st);
+    return B2S_OK;
+  }
+  B2S_REQUIRE(nbr && tile_mask && step_rows, B2S_ERR_INVALID, "b2s_tile_steps: null pointer");
+  if (tile_rows == 128) {
+    tile_steps_mask_kernel<128><<<(unsigned)tiles, 128, 0, st>>>(nbr, k, n, perm, row_bits, tile_mask, step_start);
+  } else {
+    tile_steps_mask_kernel<256><<<(unsigned)tiles, 256, 0, st>>>(nbr, k, n, perm, row_bits, tile_mask, step_start);
+  }
+  tile_steps_scan_kernel<<<1, 1024, 0, st>>>(step_start, (int)tiles);
+  if (tile_rows == 128) {
+    tile_steps_fill_kernel<128><<<(unsigned)tiles, 128, 0, st>>>(nbr, k, n, perm, tile_mask, step_start, step_rows);
+  } else {
+    tile_steps_fill_kernel<256><<<(unsigned)tiles, 256, 0, st>>>(nbr, k, n, perm, tile_mask, step_start, step_rows);
+  }
+  B2S_CHECK_LAUNCH("b2s_tile_steps");
   return B2S_OK;
 }
 

@@ -116,22 +116,25 @@ class KernelMap:
     Behaves like the reference's ``[nbmaps, nbsizes, (N_in, N_out)]`` list
     (TS/nn/functional/conv.py:174-176) when indexed or unpacked; the int64 ``nbmaps``
     view is materialised lazily (one host sync) because the kernels here consume the
-    gather maps and the padded int32 pair buffer directly.
+    gather maps, their step tables and the padded int32 pair buffer directly.
     """
 
     def __init__(self, nbr_out, nbr_in, nbsizes, sizes: Tuple[int, int], symmetric: bool,
-                 mask_out=None, mask_in=None):
+                 mask_out=None, mask_in=None, coords=None, coord_shift: int = 0):
         self.nbr_out = nbr_out          # int32 [K, N_out]: input row per (offset, output row)
         self.nbr_in = nbr_in            # int32 [K, N_in ]: output row per (offset, input row) | None
-        self.mask_out = mask_out        # active-offset bits per 128-row tile of nbr_out
+        self.mask_out = mask_out        # active-offset bits per 128-row tile of nbr_out (API row order)
         self.mask_in = mask_in          # ... of nbr_in
         self.nbsizes32 = nbsizes        # int32 [K] on device
         self.sizes = sizes
         self.symmetric = symmetric      # nbr_in[k] == nbr_out[K-1-k] (submanifold, odd kernel)
         self.kvol = nbr_out.shape[0]
-        # optional tile composition for the gather-GEMM kernels: rows re-grouped so that the
-        # 128-row tiles are spatially coherent (fewer active offsets per tile, see _tile_order)
-        self.tile_nbr = self.tile_mask = self.tile_perm = None
+        self._coords, self._shift = coords, coord_shift
+        # tile composition of the tensor-core kernels (symmetric maps): launch row j = map column perm[j],
+        # rows with equal neighbourhood patterns share tiles (see _tile_order / b2s_tile_order_key)
+        self._perm_ready = False
+        self.tile_perm = self._row_bits = None
+        self._steps = {}                # (which map, tile_rows) -> step table
         self._pairs = None              # (int32 [K*N_out, 2] padded, int64 [1] total)
         self._ref = None
 
@@ -144,18 +147,41 @@ class KernelMap:
         """Device scalar with the pair count M (used by the measurement hooks only)."""
         return self.pairs()[1] if B.PROFILER is not None else None
 
-    def out_gather_map(self):
-        """(map [K, rows], tile mask, row order | None) used to compute the OUTPUT rows."""
-        if self.tile_nbr is not None:
-            return self.tile_nbr, self.tile_mask, self.tile_perm
-        return self.nbr_out, self.mask_out, None
+    def _ensure_perm(self):
+        if self._perm_ready:
+            return
+        self._perm_ready = True
+        n = self.nbr_out.shape[1]
+        if not self.symmetric or _TILE_ORDER == "none" or n <= 256 or self._coords is None:
+            return
+        if _TILE_ORDER == "mask" and self.kvol <= 27:
+            # rows with the same neighbourhood pattern share tiles (rarest offsets first), see
+            # b2s_tile_order_key: 25 % of the (tile, offset) steps stay active at stride 1 vs 61 % for (z,x,y)
+            keys, self._row_bits = B.tile_order_key(self.nbr_out, self.nbsizes32, self._coords, self._shift)
+            self.tile_perm = torch.argsort(keys).int()
+        else:
+            self.tile_perm = _tile_order(self._coords)
 
-    def in_gather_map(self):
-        """(map [K, N_in], flip_k, tile mask, row order | None): per input row, the output row it feeds."""
-        if self.symmetric:
-            nbr, mask, perm = self.out_gather_map()
-            return nbr, True, mask, perm
-        return self.nbr_in, False, self.mask_in, None
+    def gather_args(self, which: str, feats: torch.Tensor, c_red: int, c_res: int):
+        """Keyword arguments of B.conv_gather_gemm for computing the rows of side ``which`` ("out": one row
+        per output coordinate from input rows; "in": one row per input coordinate from output rows) plus the
+        row count: step table + tile order on the fp16 tensor-core path, the plain gather map otherwise."""
+        n_rows = self.sizes[1] if which == "out" else self.sizes[0]
+        base, flip = ("out", True) if (which == "in" and self.symmetric) else (which, False)
+        nbr = self.nbr_out if base == "out" else self.nbr_in
+        if B.conv_steps_supported(feats, c_red, c_res):
+            perm = None
+            if base == "out":
+                self._ensure_perm()
+                perm = self.tile_perm
+            tr = B.conv_tile_rows(c_res, n_rows)
+            steps = self._steps.get((base, tr))
+            if steps is None:
+                steps = B.tile_steps(nbr, perm, self._row_bits if base == "out" else None, tr)
+                self._steps[(base, tr)] = steps
+            return n_rows, dict(nbr=None, steps=steps, row_perm=perm, flip_k=flip)
+        mask = self.mask_out if base == "out" else self.mask_in
+        return n_rows, dict(nbr=nbr, tile_mask=mask, row_perm=None, flip_k=flip)
 
     def reference_format(self):
         if self._ref is None:
@@ -201,53 +227,71 @@ def build_kernel_map(in_coords: torch.Tensor, out_coords: torch.Tensor, kernel_s
     symmetric = bool(same and all(k % 2 == 1 for k in kernel_size))
     nbr_out, nbr_in, nbsizes, mask_out, mask_in = B.kmap_build(in_coords, out_coords, offsets,
                                                                want_nbr_in=not symmetric)
-    km = KernelMap(nbr_out, nbr_in, nbsizes, (in_coords.shape[0], out_coords.shape[0]), symmetric,
-                   mask_out, mask_in)
-    if symmetric and _TILE_ORDER in ("zxy", "mask") and out_coords.shape[0] > 256:
-        if _TILE_ORDER == "mask" and offsets.shape[0] <= 27:
-            # rows with the same neighbourhood pattern share tiles (rarest offsets first), see
-            # b2s_tile_order_key: halves the active (tile, offset) steps again vs the (z,x,y) order
-            shift = max(int(in_stride[0]).bit_length() - 1, 0) if not isinstance(in_stride, int) \
-                else max(int(in_stride).bit_length() - 1, 0)
-            perm = torch.argsort(B.tile_order_key(nbr_out, nbsizes, out_coords, shift)).int()
-        else:
-            perm = _tile_order(out_coords)
-        km.tile_perm = perm
-        km.tile_nbr = nbr_out.index_select(1, perm.long()).contiguous()
-        km.tile_mask = B.tile_mask(km.tile_nbr)
-    return km
+    s0 = int(in_stride[0]) if not isinstance(in_stride, int) else int(in_stride)
+    return KernelMap(nbr_out, nbr_in, nbsizes, (in_coords.shape[0], out_coords.shape[0]), symmetric,
+                     mask_out, mask_in, coords=out_coords, coord_shift=max(s0.bit_length() - 1, 0))
 
 
 # ---------------------------------------------------------------------- convolution
-def _cast_weight(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
-    """fp32 master weight -> feature dtype, cached ON the parameter object until it is next updated
-    in place (the reference re-casts on every call through custom_fwd, TS/nn/functional/conv.py:19)."""
-    if weight.dtype == dtype:
-        return weight
-    hit = getattr(weight, "_b2s_cast", None)
-    if hit is not None and hit[0] == weight._version and hit[1] is dtype and hit[2].device == weight.device \
-            and hit[2].shape == weight.shape:
-        return hit[2]
-    w = weight.detach().to(dtype)
+def _weight_cache(weight: torch.Tensor, slot: str, make):
+    """Derived copies of a parameter (fp16 cast, K-major transpose), cached ON the parameter object until it is
+    next updated in place or re-bound (version counter + storage pointer + shape are the key)."""
     try:
-        weight._b2s_cast = (weight._version, dtype, w)
+        key = (weight._version, weight.data_ptr(), tuple(weight.shape), weight.device)
+    except RuntimeError:                                    # inference tensors have no version counter
+        return make()
+    hit = weight.__dict__.get(slot) if hasattr(weight, "__dict__") else None
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    val = make()
+    try:
+        setattr(weight, slot, (key, val))
     except AttributeError:
         pass
-    return w
+    return val
 
 
-def _gather_gemm_wide(feats, w, gmap, n_rows, transpose_w, flip, **kw):
-    """conv_gather_gemm with result widths above the kernel's 512 TMEM columns split into column
-    blocks of the weight (e.g. the input gradient of RPVNet's 672 -> 448 decoder conv)."""
-    c_res = w.shape[1] if transpose_w else w.shape[2]
+def _cast_weight(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """fp32 master weight -> feature dtype (the reference re-casts on every call through custom_fwd,
+    TS/nn/functional/conv.py:19)."""
+    if weight.dtype == dtype:
+        return weight
+    return _weight_cache(weight, "_b2s_cast_" + str(dtype).split(".")[-1], lambda: weight.detach().to(dtype))
+
+
+def _kmajor_weight(weight: torch.Tensor, w_cast: torch.Tensor):
+    """The forward pass's K-major operand [K, C_out, C_in] of an fp16 weight, cached with the parameter (the
+    first revision transposed the weight inside every forward call: 63 extra launches per step)."""
+    if w_cast.dtype != torch.float16:
+        return None
+    w3 = w_cast if w_cast.ndim == 3 else w_cast.unsqueeze(0)
+    return _weight_cache(weight, "_b2s_kmajor", lambda: B.weight_to_kmajor(w3.contiguous()))
+
+
+def _conv_rows(feats, w, kmap: Optional[KernelMap], which: str, transpose_w: bool, w_kmajor=None, hint=None,
+               bn_sums=None):
+    """Rows of side ``which`` of ``kmap`` (None: identity map / 1x1 conv) = gather-GEMM of ``feats`` with ``w``
+    [K, C_in, C_out]; result widths above the kernel's 512 TMEM columns are split into column blocks of the
+    weight (e.g. the input gradient of RPVNet's 672 -> 448 decoder conv)."""
+    c_red, c_res = (w.shape[2], w.shape[1]) if transpose_w else (w.shape[1], w.shape[2])
+
+    def run(wb, width, kmajor, sums):
+        if kmap is None:
+            return B.conv_gather_gemm(feats, wb, None, feats.shape[0], transpose_w, False, pairs_hint=hint,
+                                      weight_kmajor=kmajor, bn_sums=sums)
+        n_rows, kw = kmap.gather_args(which, feats, c_red, width)
+        return B.conv_gather_gemm(feats, wb, n_rows=n_rows, transpose_w=transpose_w, pairs_hint=hint,
+                                  weight_kmajor=kmajor, bn_sums=sums if "steps" in kw else None, **kw)
+
     if c_res <= 512 or feats.dtype != torch.float16:
-        return B.conv_gather_gemm(feats, w, gmap, n_rows, transpose_w, flip, **kw)
+        return run(w, c_res, w_kmajor, bn_sums)
+    assert bn_sums is None
     n_blk = -(-c_res // 512)
     step = -(-c_res // (n_blk * 32)) * 32
     outs = []
     for c0 in range(0, c_res, step):
         wb = (w[:, c0:c0 + step, :] if transpose_w else w[:, :, c0:c0 + step]).contiguous()
-        outs.append(B.conv_gather_gemm(feats, wb, gmap, n_rows, transpose_w, flip, **kw))
+        outs.append(run(wb, wb.shape[1] if transpose_w else wb.shape[2], None, None))
     return torch.cat(outs, dim=1)
 
 
@@ -259,18 +303,11 @@ class ConvolutionFunction(Function):
     """
 
     @staticmethod
-    def forward(ctx, feats, weight, kmap: KernelMap, transposed: bool):
+    def forward(ctx, feats, weight, kmap: KernelMap, transposed: bool, bn_sums=None):
         feats = feats.contiguous()
         w = _cast_weight(weight, feats.dtype)
-        hint = kmap.total_hint()
-        if not transposed:
-            gmap, mask, perm = kmap.out_gather_map()
-            out = _gather_gemm_wide(feats, w, gmap, kmap.sizes[1], False, False, pairs_hint=hint,
-                                    tile_mask=mask, row_perm=perm)
-        else:
-            gmap, flip, mask, perm = kmap.in_gather_map()
-            out = _gather_gemm_wide(feats, w, gmap, kmap.sizes[0], False, flip, pairs_hint=hint,
-                                    tile_mask=mask, row_perm=perm)
+        out = _conv_rows(feats, w, kmap, "in" if transposed else "out", False, _kmajor_weight(weight, w),
+                         kmap.total_hint(), bn_sums)
         ctx.save_for_backward(feats, weight)
         ctx.kmap, ctx.transposed = kmap, transposed
         return out
@@ -285,20 +322,13 @@ class ConvolutionFunction(Function):
         grad_in = grad_w = None
         hint = kmap.total_hint()
         if ctx.needs_input_grad[0]:
-            if not transposed:
-                gmap, flip, mask, perm = kmap.in_gather_map()
-                grad_in = _gather_gemm_wide(grad_out, w, gmap, kmap.sizes[0], True, flip, pairs_hint=hint,
-                                            tile_mask=mask, row_perm=perm)
-            else:
-                gmap, mask, perm = kmap.out_gather_map()
-                grad_in = _gather_gemm_wide(grad_out, w, gmap, kmap.sizes[1], True, False,
-                                            pairs_hint=hint, tile_mask=mask, row_perm=perm)
+            grad_in = _conv_rows(grad_out, w, kmap, "out" if transposed else "in", True, None, hint)
         if ctx.needs_input_grad[1]:
             pairs, _ = kmap.pairs()
             grad_w = B.conv_wgrad(feats, grad_out, kmap.kvol, pairs, kmap.nbsizes32, transposed,
                                   pairs_hint=hint)
             grad_w = grad_w.to(weight.dtype)
-        return grad_in, grad_w, None, None
+        return grad_in, grad_w, None, None, None
 
 
 class _DenseConv(Function):
@@ -308,8 +338,8 @@ class _DenseConv(Function):
     def forward(ctx, feats, weight):
         feats = feats.contiguous()
         ctx.save_for_backward(feats, weight)
-        return _gather_gemm_wide(feats, _cast_weight(weight, feats.dtype).unsqueeze(0), None, feats.shape[0],
-                                 False, False)
+        w = _cast_weight(weight, feats.dtype)
+        return _conv_rows(feats, w if w.ndim == 3 else w.unsqueeze(0), None, "out", False, _kmajor_weight(weight, w))
 
     @staticmethod
     @once_differentiable
@@ -318,8 +348,8 @@ class _DenseConv(Function):
         grad_out = grad_out.contiguous()
         grad_in = grad_w = None
         if ctx.needs_input_grad[0]:
-            grad_in = _gather_gemm_wide(grad_out, _cast_weight(weight, feats.dtype).unsqueeze(0), None,
-                                        feats.shape[0], True, False)
+            w = _cast_weight(weight, feats.dtype)
+            grad_in = _conv_rows(grad_out, w if w.ndim == 3 else w.unsqueeze(0), None, "in", True)
         if ctx.needs_input_grad[1]:
             grad_w = B.conv_wgrad(feats, grad_out, 1, None, None, False)[0].to(weight.dtype)
         return grad_in, grad_w
@@ -341,12 +371,22 @@ def _pad_for_tensor_cores(feats: torch.Tensor, weight: torch.Tensor):
     return feats, weight, (c_out if pad_out else None)
 
 
+def _can_fuse_sums(bn_sums, feats, weight, keep_out, bias) -> bool:
+    return (bn_sums is not None and keep_out is None and bias is None and weight.ndim == 3
+            and weight.shape[2] <= 512 and B.conv_steps_supported(feats, weight.shape[1], weight.shape[2]))
+
+
 def conv3d(input: SparseTensor, weight: torch.Tensor,
            kernel_size: Union[int, List[int], Tuple[int, ...]], bias: Optional[torch.Tensor] = None,
            stride: Union[int, List[int], Tuple[int, ...]] = 1,
-           dilation: Union[int, Tuple[int, ...]] = 1, transposed: bool = False) -> SparseTensor:
+           dilation: Union[int, Tuple[int, ...]] = 1, transposed: bool = False,
+           bn_sums: Optional[torch.Tensor] = None) -> SparseTensor:
     """Sparse 3-D convolution with the reference's coordinate / map caching rules
-    (TS/nn/functional/conv.py:122-205)."""
+    (TS/nn/functional/conv.py:122-205).
+
+    ``bn_sums`` (extension, fp64 zeros [2, C_out]): when the fp16 step-table kernel runs this conv, its epilogue
+    adds the per-channel sum / sum of squares of the result rows into it and the result's ``feats`` carries it as
+    ``_b2s_sums`` - ``batch_norm_act`` then skips its statistics pass."""
     kernel_size = make_ntuple(kernel_size, ndim=3)
     stride = make_ntuple(stride, ndim=3)
     dilation = make_ntuple(dilation, ndim=3)
@@ -368,12 +408,18 @@ def conv3d(input: SparseTensor, weight: torch.Tensor,
         if key not in input.kmaps:
             input.kmaps[key] = build_kernel_map(input.coords, out_coords, kernel_size, input.stride,
                                                 dilation)
-        out_feats = ConvolutionFunction.apply(feats, weight, input.kmaps[key], False)
+        fuse = _can_fuse_sums(bn_sums, feats, weight, keep_out, bias)
+        out_feats = ConvolutionFunction.apply(feats, weight, input.kmaps[key], False, bn_sums if fuse else None)
+        if fuse:
+            out_feats._b2s_sums = bn_sums
     else:
         out_stride = tuple(input.stride[a] // stride[a] for a in range(3))
         out_coords = input.cmaps[out_stride]
         kmap = input.kmaps[(out_stride, kernel_size, stride, dilation)]
-        out_feats = ConvolutionFunction.apply(feats, weight, kmap, True)
+        fuse = _can_fuse_sums(bn_sums, feats, weight, keep_out, bias)
+        out_feats = ConvolutionFunction.apply(feats, weight, kmap, True, bn_sums if fuse else None)
+        if fuse:
+            out_feats._b2s_sums = bn_sums
 
     if keep_out is not None:
         # contiguous: a strided [N, C] view sends torch's batch norm to its generic (non channels-last)
@@ -404,9 +450,9 @@ class _BatchNormAct(Function):
     """y = act(batch_norm_train(x) [+ residual]) in two kernels forward / two backward."""
 
     @staticmethod
-    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, eps, momentum, relu):
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, eps, momentum, relu, sums=None):
         y, mean, invstd = B.bn_forward(x, residual, gamma, beta, running_mean, running_var, eps, momentum,
-                                       relu)
+                                       relu, sums)
         ctx.save_for_backward(x, y if relu else None, mean, invstd, gamma)
         ctx.relu, ctx.has_res = relu, residual is not None
         ctx.mark_non_differentiable(mean, invstd)
@@ -419,7 +465,7 @@ class _BatchNormAct(Function):
         dx, dres, dgamma, dbeta = B.bn_backward(dy, y, x, mean, invstd, gamma, ctx.relu,
                                                 ctx.has_res and ctx.needs_input_grad[1])
         return (dx, dres, dgamma.to(gamma.dtype) if gamma is not None else None,
-                dbeta.to(gamma.dtype) if gamma is not None else None, None, None, None, None, None)
+                dbeta.to(gamma.dtype) if gamma is not None else None, None, None, None, None, None, None)
 
 
 def batch_norm_act(x: torch.Tensor, bn: torch.nn.modules.batchnorm._BatchNorm, relu: bool = False,
@@ -441,4 +487,13 @@ def batch_norm_act(x: torch.Tensor, bn: torch.nn.modules.batchnorm._BatchNorm, r
     with torch.no_grad():
         bn.num_batches_tracked += 1
     return _BatchNormAct.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
-                               bn.momentum, relu)
+                               bn.momentum, relu, getattr(x, "_b2s_sums", None))
+
+
+def batch_norm_fusable(x_dtype: torch.dtype, bn: torch.nn.modules.batchnorm._BatchNorm) -> bool:
+    """Whether ``batch_norm_act`` will take its fused training path for this module (then the producing conv may
+    accumulate the statistics, ``conv3d(bn_sums=...)``)."""
+    sync = isinstance(bn, torch.nn.SyncBatchNorm) and torch.distributed.is_available() and \
+        torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
+    return bool(bn.training and not sync and bn.track_running_stats and bn.momentum is not None
+                and x_dtype == torch.float16)

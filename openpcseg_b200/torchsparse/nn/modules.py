@@ -53,9 +53,10 @@ class Conv3d(nn.Module):
             parts.append("transposed=True")
         return ", ".join(parts)
 
-    def forward(self, input: SparseTensor) -> SparseTensor:
+    def forward(self, input: SparseTensor, bn_sums=None) -> SparseTensor:
         return F.conv3d(input, self.kernel, kernel_size=self.kernel_size, bias=self.bias,
-                        stride=self.stride, dilation=self.dilation, transposed=self.transposed)
+                        stride=self.stride, dilation=self.dilation, transposed=self.transposed,
+                        bn_sums=bn_sums)
 
 
 class BatchNorm(nn.BatchNorm1d):

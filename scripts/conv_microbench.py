@@ -58,17 +58,19 @@ def main():
         x = torch.randn(n, cin, device=dev, dtype=torch.float16)
         gy = torch.randn(n, cout, device=dev, dtype=torch.float16)
         w = (torch.randn(27, cin, cout, device=dev) / (27 * cin) ** 0.5).half()
-        omap, omask, operm = km.out_gather_map()
-        gmap, flip, gmask, gperm = km.in_gather_map()
+        _, okw = km.gather_args("out", x, cin, cout)
+        _, gkw = km.gather_args("in", gy, cout, cin)
+        wk = B.weight_to_kmajor(w)
         runs = {
-            "fwd": lambda: B.conv_gather_gemm(x, w, omap, n, False, False, tile_mask=omask, row_perm=operm),
-            "dgrad": lambda: B.conv_gather_gemm(gy, w, gmap, n, True, flip, tile_mask=gmask, row_perm=gperm),
+            "fwd": lambda: B.conv_gather_gemm(x, w, n_rows=n, transpose_w=False, weight_kmajor=wk, **okw),
+            "dgrad": lambda: B.conv_gather_gemm(gy, w, n_rows=n, transpose_w=True, **gkw),
             "wgrad": lambda: B.conv_wgrad(x, gy, 27, pairs, km.nbsizes32, False),
         }
+        omask = okw["steps"][0] if "steps" in okw else None
         if omask is not None and name[:2] not in seen_levels:
             seen_levels.add(name[:2])
             steps = sum(bin(v & 0xFFFFFFFF).count("1") for v in omask.cpu().flatten().tolist())
-            tiles = (n + 127) // 128
+            tiles = omask.shape[0]
             print(f"# {name[:2]}: {tiles} row tiles, {steps} active (tile, offset) steps = "
                   f"{steps / (27.0 * tiles):.3f} of 27/tile; pairs/step {m / max(steps, 1):.1f} of 128")
         useful = 2.0 * m * cin * cout

@@ -183,3 +183,43 @@ def test_full_size_fp16_tensor_core_path_against_fp32_path():
     ref, out = run(False), run(True)
     for a, b in zip(out, ref):
         assert float((a - b).abs().max()) <= 1e-3 * float(b.abs().max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cin,cout", [(96, 96), (256, 256), (32, 32), (128, 96)])
+def test_full_size_fp16_conv_against_the_reference_cpu_backend(cin, cout):
+    """BASELINE-size (2 scans, ~190 k voxels = ~1500 row tiles per launch: the persistent multi-tile loop, ring
+    wrap-around across tiles, TMEM accumulator turn-taking and the row_perm epilogue) fp16 tensor-core forward,
+    input gradient and weight gradient against an INDEPENDENT answer: the reference's own compiled CPU backend
+    (oracle/_ref: convolution_forward_cpu / convolution_backward_cpu, fp32) on the same fp16-representable
+    operands and the same reference-format pair list.  Bar: 1e-3 of the result's max (north_star, fp16)."""
+    import openpcseg_b200.torchsparse as ts
+    from oracle import build_ref
+    F = ts.nn.functional
+    ref = build_ref.load()
+    if ref is None:
+        pytest.skip("oracle/_ref (reference CPU backend) is not built")
+    torch.set_num_threads(8)
+    c = _full_batch()
+    n = c.shape[0]
+    g = torch.Generator(device="cuda").manual_seed(cin + cout)
+    h = lambda t: t.half().float()
+    x = h(torch.randn(n, cin, device="cuda", generator=g))
+    w = h(torch.randn(27, cin, cout, device="cuda", generator=g) / (27 * cin) ** 0.5 * 3)
+    go = h(torch.randn(n, cout, device="cuda", generator=g))
+    xt, wl = x.half().requires_grad_(True), w.clone().requires_grad_(True)
+    st = ts.SparseTensor(xt, c, 1)
+    st.cmaps[st.stride] = st.coords
+    with torch.autocast("cuda", dtype=torch.float16):
+        y = F.conv3d(st, wl, 3)
+    y.feats.backward(go.half())
+    nbmaps, nbsizes, _ = y.kmaps[((1, 1, 1), (3, 3, 3), (1, 1, 1), (1, 1, 1))]
+    nb, ns = nbmaps.int().cpu().contiguous(), nbsizes.int().cpu().contiguous()
+    xc, wc, gc = x.cpu(), w.cpu(), go.cpu()
+    out = torch.zeros(n, cout)
+    ref.convolution_forward_cpu(xc, out, wc, nb, ns, False)
+    gi, gw = torch.zeros_like(xc), torch.zeros_like(wc)
+    ref.convolution_backward_cpu(xc, gi, gc, wc, gw, nb, ns, False)
+    for name, a, b in (("fwd", y.feats, out), ("dgrad", xt.grad, gi), ("wgrad", wl.grad, gw)):
+        err = float((a.float().cpu() - b).abs().max() / b.abs().max())
+        assert err <= 1e-3, (name, cin, cout, err)
