@@ -77,10 +77,15 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference_cuda"])
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "fp32"])
     ap.add_argument("--sync-bn", action="store_true")
+    ap.add_argument("--sm-reserve", type=int, default=None,
+                    help="SMs kept free of the persistent conv grids (default 0: measured at N = 2, reserving 8 / 16 "
+                         "SMs for NCCL LOSES 3 % - the all-reduce is not what limits scaling, profiles/r2_scaling.txt)")
     ap.add_argument("--pool", type=int, default=4, help="distinct batches cycled per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-config1", action="store_true")
+    ap.add_argument("--same-data", action="store_true",
+                    help="diagnostic: every rank gets rank 0's scans (separates load imbalance from communication)")
     ap.add_argument("--cpu-budget-s", type=float, default=None,
                     help="CPU seconds for the reference arm (default 150 for --impl reference, 25 for the "
                          "cpu_baseline leg of the default run)")
@@ -362,8 +367,12 @@ def main():
     from openpcseg_b200.synthetic import make_model_batch
     ours = args.impl == "ours"
     B = None
+    reserve = 0
     if ours:
         from openpcseg_b200 import backend as B
+        # DDP: NCCL's all-reduce kernels need SMs while the backward's persistent grids are resident
+        reserve = args.sm_reserve if args.sm_reserve is not None else 0
+        B.set_sm_reserve(reserve)
 
     torch.manual_seed(0)
     amp = args.dtype == "fp16"
@@ -380,7 +389,7 @@ def main():
     model.train()
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local])
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
     # SGD momentum 0.9, weight decay 1e-4 (pcseg/optim/__init__.py:15-21 - the reference never passes
     # NESTEROV on), AMP GradScaler, clip 10 (train.py:367-372); lr is irrelevant to throughput
     opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
@@ -390,7 +399,7 @@ def main():
     unit_key = "voxel_coord" if kind == "cylinder" else "coords"
     pool = []
     for p in range(args.pool):
-        seeds = D.scan_seeds(rank, p, args.batch)
+        seeds = D.scan_seeds(0 if args.same_data else rank, p, args.batch)
         b = make_model_batch(kind, seeds)
         pool.append({k: torch.from_numpy(v).pin_memory() for k, v in b.items() if isinstance(v, np.ndarray)})
     vox_per_scan = float(np.mean([p[unit_key].shape[0] for p in pool])) / args.batch
@@ -521,7 +530,8 @@ def main():
             "config": {"workload": workload, "name": args.config, "model_src": args.model_src,
                        "scans_per_gpu_per_step": args.batch, "voxels_per_scan": int(vox_per_scan),
                        "amp": amp, "sync_bn": bool(args.sync_bn and world > 1),
-                       "parallelism": f"dp{world}", "l2": "256 MiB flush write before every step",
+                       "parallelism": f"dp{world}", "sm_reserve": reserve,
+                       "l2": "256 MiB flush write before every step",
                        "peaks": pk},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

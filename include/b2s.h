@@ -44,6 +44,10 @@ enum b2s_dtype { B2S_F32 = 0, B2S_F16 = 1 };
 
 const char* b2s_last_error(void);
 int b2s_version(void);
+/* Leave `n` SMs free of the persistent convolution grids (default 0, or env B2S_SM_RESERVE): under
+ * data-parallel training NCCL's all-reduce CTAs then start at once instead of queueing behind a grid that
+ * fills every SM slot for the length of a kernel.  Process-wide, not stream-ordered.                  */
+void b2s_set_sm_reserve(int32_t n);
 
 /* ---------------------------------------------------------------- hashing ---
  * replaces hash_cuda / kernel_hash_cuda (TS/backend/hash/hash_cuda.cu:67-84).
@@ -116,6 +120,15 @@ int b2s_kmap_build(const int32_t* in_coords, int64_t n_in, const int32_t* out_co
                    uint32_t* tile_mask_in, void* ws, size_t ws_bytes, b2s_stream_t stream);
 int b2s_kmap_pairs(const int32_t* nbr_out, int32_t k, int64_t n_out, int32_t* nbmaps,
                    int64_t* d_total, void* ws, size_t ws_bytes, b2s_stream_t stream);
+/* The same pair list in (chunk, offset, row) order for the weight gradient: the n_out rows - taken in the order
+ * perm (NULL: as stored) - are cut into n_chunks equal ranges and all K offsets of a range are adjacent, so the
+ * X / dY rows of a range are reused from L2 across its offsets instead of being re-read from HBM once per offset
+ * (with perm = a spatial order of the rows also across neighbouring rows).  seg_sizes int32 [n_chunks * K]
+ * (segment c*K + k = pairs of offset k in range c) replaces nbsizes in b2s_conv_wgrad_segments.          */
+size_t b2s_kmap_pairs_chunked_workspace_bytes(int64_t n_out, int32_t k, int32_t n_chunks);
+int b2s_kmap_pairs_chunked(const int32_t* nbr_out, int32_t k, int64_t n_out, const int32_t* perm,
+                           int32_t n_chunks, int32_t* nbmaps, int32_t* seg_sizes, int64_t* d_total, void* ws,
+                           size_t ws_bytes, b2s_stream_t stream);
 /* active-offset masks of the 128-row tiles of an arbitrary gather map nbr [K, n] (e.g. a
  * column-permuted copy of nbr_out): tile_mask uint32 [ceil(n/128)][ceil(K/32)].           */
 int b2s_tile_mask(const int32_t* nbr, int32_t k, int64_t n, uint32_t* tile_mask, b2s_stream_t stream);
@@ -194,6 +207,12 @@ int b2s_conv_wgrad(int32_t dtype, const void* in, int64_t n_in, const void* grad
                    int64_t n_out, int32_t k, int32_t c_in, int32_t c_out, const int32_t* nbmaps,
                    const int32_t* nbsizes, int32_t swap_pairs, float* grad_w, void* ws,
                    size_t ws_bytes, b2s_stream_t stream);
+/* b2s_conv_wgrad over a segmented pair list (b2s_kmap_pairs_chunked): n_seg = n_chunks * K consecutive segments
+ * of seg_sizes[s] pairs, segment s belonging to offset s % K.  n_seg <= 1024.                           */
+int b2s_conv_wgrad_segments(int32_t dtype, const void* in, int64_t n_in, const void* grad_out,
+                            int64_t n_out, int32_t k, int32_t c_in, int32_t c_out, const int32_t* nbmaps,
+                            const int32_t* seg_sizes, int32_t n_seg, int32_t swap_pairs, float* grad_w,
+                            b2s_stream_t stream);
 
 /* --------------------------------------------------------- point <-> voxel ---
  * replaces voxelize_{forward,backward}_cuda (TS/backend/voxelize/voxelize_cuda.cu:44-80)
@@ -212,6 +231,13 @@ int b2s_devoxelize_fwd(int32_t dtype, const void* feats, const int32_t* idx /*[n
 int b2s_devoxelize_bwd(int32_t dtype, const void* grad_pts, const int32_t* idx,
                        const float* weights, int64_t n_pts, int64_t n_vox, int32_t c,
                        void* grad_vox, float* acc, b2s_stream_t stream);
+/* b2s_devoxelize_bwd for contended maps (many points per voxel: coarse strides).  `order` int32 [n_pts] is a
+ * permutation of the points sorted by their corner-0 voxel (idx[:, 0]); consecutive points then share corners
+ * and their contributions are summed in registers before ONE vector red per (corner, run).  Same result up to
+ * fp32 summation order.  Needs C to be a multiple of the 16-byte vector (8 fp16 / 4 fp32 channels).        */
+int b2s_devoxelize_bwd_sorted(int32_t dtype, const void* grad_pts, const int32_t* order, const int32_t* idx,
+                              const float* weights, int64_t n_pts, int64_t n_vox, int32_t c, void* grad_vox,
+                              float* acc, b2s_stream_t stream);
 
 /* Scatter-max of point rows into voxel rows (Cylinder3D's torch_scatter.scatter_max,
  * tools/utils/common/seg_utils.py:172-188, pcseg/model/segmentor/voxel/cylinder3d/
@@ -253,6 +279,19 @@ int b2s_bn_forward_sums(int32_t dtype, const void* x, const void* residual, int6
                         float* running_mean, float* running_var, int32_t relu, void* y, float* mean,
                         float* invstd, float* scale_shift, double* sums, int32_t sums_ready,
                         b2s_stream_t stream);
+/* Pieces of the two calls above for SYNCHRONISED batch norm (the reference's IF_DIST: True): the caller
+ * all-reduces the fp64 sums between them.  b2s_bn_stats: sums[2][c] = per-channel (sum, sum of squares) of x.
+ * b2s_bn_forward_sums with sums_ready == 2: sums has 2c + 1 entries, the last one the GLOBAL row count.
+ * b2s_bn_backward_reduce: sums[2][c] = (sum dy', sum dy' * xhat) of the local rows (= d_beta, d_gamma);
+ * b2s_bn_backward_apply: dx (and dres) from all-reduced sums and the global count n_total (device fp64; NULL:
+ * the local n).                                                                                          */
+int b2s_bn_stats(int32_t dtype, const void* x, int64_t n, int32_t c, double* sums, b2s_stream_t stream);
+int b2s_bn_backward_reduce(int32_t dtype, const void* dy, const void* y, const void* x, int64_t n, int32_t c,
+                           const float* mean, const float* invstd, int32_t relu, double* sums,
+                           b2s_stream_t stream);
+int b2s_bn_backward_apply(int32_t dtype, const void* dy, const void* y, const void* x, int64_t n, int32_t c,
+                          const float* mean, const float* invstd, const float* gamma, int32_t relu, void* dx,
+                          void* dres, const double* sums, const double* n_total, b2s_stream_t stream);
 int b2s_bn_backward(int32_t dtype, const void* dy, const void* y, const void* x, int64_t n, int32_t c,
                     const float* mean, const float* invstd, const float* gamma, int32_t relu, void* dx,
                     void* dres, double* sums, b2s_stream_t stream);

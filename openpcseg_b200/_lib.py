@@ -18,6 +18,7 @@ _SIGNATURES = {
     # name: (restype, [argtypes])
     "b2s_last_error": (c_char_p, []),
     "b2s_version": (c_int32, []),
+    "b2s_set_sm_reserve": (None, [c_int32]),
     "b2s_hash": (c_int32, [_P, c_int64, _P, _P]),
     "b2s_kernel_hash": (c_int32, [_P, c_int64, _P, c_int32, _P, _P]),
     "b2s_table_slots": (c_int64, [c_int64]),
@@ -35,6 +36,10 @@ _SIGNATURES = {
     "b2s_kmap_build": (c_int32, [_P, c_int64, _P, c_int64, _P, c_int32, _P, _P, _P, _P, _P, _P, c_size_t,
                                  _P]),
     "b2s_kmap_pairs": (c_int32, [_P, c_int32, c_int64, _P, _P, _P, c_size_t, _P]),
+    "b2s_kmap_pairs_chunked_workspace_bytes": (c_size_t, [c_int64, c_int32, c_int32]),
+    "b2s_kmap_pairs_chunked": (c_int32, [_P, c_int32, c_int64, _P, c_int32, _P, _P, _P, _P, c_size_t, _P]),
+    "b2s_conv_wgrad_segments": (c_int32, [c_int32, _P, c_int64, _P, c_int64, c_int32, c_int32, c_int32, _P, _P,
+                                          c_int32, c_int32, _P, _P]),
     "b2s_conv_workspace_bytes": (c_size_t, [c_int32, c_int64, c_int32, c_int32, c_int32]),
     "b2s_conv_gather_gemm": (c_int32, [c_int32, _P, c_int64, _P, c_int32, c_int32, c_int32, c_int32,
                                        c_int32, _P, _P, _P, c_int64, _P, _P, _P, c_size_t, _P]),
@@ -54,6 +59,7 @@ _SIGNATURES = {
     "b2s_voxelize_bwd": (c_int32, [c_int32, _P, _P, _P, c_int64, c_int64, c_int32, _P, _P]),
     "b2s_devoxelize_fwd": (c_int32, [c_int32, _P, _P, _P, c_int64, c_int64, c_int32, _P, _P]),
     "b2s_devoxelize_bwd": (c_int32, [c_int32, _P, _P, _P, c_int64, c_int64, c_int32, _P, _P, _P]),
+    "b2s_devoxelize_bwd_sorted": (c_int32, [c_int32, _P, _P, _P, _P, c_int64, c_int64, c_int32, _P, _P, _P]),
     "b2s_scatter_max": (c_int32, [c_int32, _P, _P, c_int64, c_int32, c_int64, _P, _P, _P, _P]),
     "b2s_trilinear_map": (c_int32, [_P, c_int64, c_int32, _P, c_int64, _P, _P, _P]),
     "b2s_ti_weights": (c_int32, [_P, c_int64, _P, c_float, _P, _P]),
@@ -62,6 +68,10 @@ _SIGNATURES = {
                                  c_int32, _P, _P, _P, _P, _P, _P]),
     "b2s_bn_forward_sums": (c_int32, [c_int32, _P, _P, c_int64, c_int32, _P, _P, c_float, c_float, _P, _P,
                                       c_int32, _P, _P, _P, _P, _P, c_int32, _P]),
+    "b2s_bn_stats": (c_int32, [c_int32, _P, c_int64, c_int32, _P, _P]),
+    "b2s_bn_backward_reduce": (c_int32, [c_int32, _P, _P, _P, c_int64, c_int32, _P, _P, c_int32, _P, _P]),
+    "b2s_bn_backward_apply": (c_int32, [c_int32, _P, _P, _P, c_int64, c_int32, _P, _P, _P, c_int32, _P, _P, _P, _P,
+                                        _P]),
     "b2s_bn_backward": (c_int32, [c_int32, _P, _P, _P, c_int64, c_int32, _P, _P, _P, c_int32, _P, _P, _P,
                                   _P]),
     "b2s_map_count": (c_int32, [_P, c_int64, c_int32, c_int32, c_int32, _P, _P]),

@@ -47,6 +47,11 @@ class _Timed:
         return False
 
 
+def set_sm_reserve(n: int) -> None:
+    """Keep ``n`` SMs free of the persistent conv grids (room for NCCL under DDP); b2s_set_sm_reserve."""
+    _lib.lib().b2s_set_sm_reserve(int(n))
+
+
 def check(rc: int, what: str = "", launches: int = 1) -> None:
     _check(rc, what)
     STATS["launches"] += launches
@@ -302,6 +307,24 @@ def kmap_pairs(nbr_out: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     return pairs, total
 
 
+def kmap_pairs_chunked(nbr_out: torch.Tensor, perm: Optional[torch.Tensor], n_chunks: int):
+    """(pairs int32 [K*N_out, 2] padded, seg_sizes int32 [n_chunks * K], d_total int64 [1]): the pair list in
+    (row range, offset, row) order for the weight gradient (b2s_kmap_pairs_chunked)."""
+    _cuda(nbr_out, perm)
+    k, n_out = nbr_out.shape
+    dev = nbr_out.device
+    pairs = torch.empty((max(k * n_out, 1), 2), dtype=torch.int32, device=dev)
+    seg = torch.empty(n_chunks * k, dtype=torch.int32, device=dev)
+    total = torch.empty(1, dtype=torch.int64, device=dev)
+    L = _lib.lib()
+    nbytes = L.b2s_kmap_pairs_chunked_workspace_bytes(n_out, k, int(n_chunks))
+    ws = _ws(nbytes, dev)
+    check(L.b2s_kmap_pairs_chunked(nbr_out.data_ptr(), k, n_out, _ptr(perm), int(n_chunks), pairs.data_ptr(),
+                                   seg.data_ptr(), total.data_ptr(), ws.data_ptr(), nbytes, _stream()),
+          "kmap_pairs_chunked", launches=2)
+    return pairs, seg, total
+
+
 # --------------------------------------------------------------------- convolution
 def conv_gather_gemm(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[torch.Tensor],
                      n_rows: int, transpose_w: bool, flip_k: bool,
@@ -358,7 +381,8 @@ def conv_gather_gemm(feats: torch.Tensor, weight: torch.Tensor, nbr: Optional[to
 
 def conv_wgrad(feats: torch.Tensor, grad_out: torch.Tensor, k: int, pairs: Optional[torch.Tensor],
                nbsizes: Optional[torch.Tensor], swap_pairs: bool, pairs_hint=None) -> torch.Tensor:
-    """fp32 grad_w [K, C_in, C_out]; pairs/nbsizes stay on the device (no sync)."""
+    """fp32 grad_w [K, C_in, C_out]; pairs/nbsizes stay on the device (no sync).  ``nbsizes`` with n_chunks * K
+    entries = the segment sizes of a ``kmap_pairs_chunked`` list."""
     _cuda(feats, grad_out, pairs, nbsizes)
     feats, grad_out = feats.contiguous(), grad_out.contiguous()
     assert feats.dtype == grad_out.dtype
@@ -366,10 +390,11 @@ def conv_wgrad(feats: torch.Tensor, grad_out: torch.Tensor, k: int, pairs: Optio
     gw = torch.empty((k, c_in, c_out), dtype=torch.float32, device=feats.device)
     with _Timed("wgrad", {"k": k, "c_in": c_in, "c_out": c_out, "rows": feats.shape[0],
                           "dtype": _dtype_code(feats), "pairs": pairs_hint}):
-        check(_lib.lib().b2s_conv_wgrad(_dtype_code(feats), feats.data_ptr(), feats.shape[0],
-                                        grad_out.data_ptr(), grad_out.shape[0], k, c_in, c_out,
-                                        _ptr(pairs), _ptr(nbsizes), int(swap_pairs), gw.data_ptr(), None,
-                                        0, _stream()), "conv_wgrad")
+        n_seg = int(nbsizes.numel()) if nbsizes is not None else k
+        check(_lib.lib().b2s_conv_wgrad_segments(_dtype_code(feats), feats.data_ptr(), feats.shape[0],
+                                                 grad_out.data_ptr(), grad_out.shape[0], k, c_in, c_out,
+                                                 _ptr(pairs), _ptr(nbsizes), n_seg, int(swap_pairs),
+                                                 gw.data_ptr(), _stream()), "conv_wgrad")
     return gw
 
 
@@ -414,7 +439,8 @@ def devoxelize_forward(feats: torch.Tensor, idx: torch.Tensor, weights: torch.Te
 
 
 def devoxelize_backward(grad_pts: torch.Tensor, idx: torch.Tensor, weights: torch.Tensor,
-                        n_vox: int) -> torch.Tensor:
+                        n_vox: int, order: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``order`` int32 [n_pts] (points sorted by idx[:, 0]) selects the run-merging kernel for contended maps."""
     _cuda(grad_pts, idx, weights)
     grad_pts, idx = grad_pts.contiguous(), idx.contiguous()
     weights = weights.float().contiguous()
@@ -422,6 +448,12 @@ def devoxelize_backward(grad_pts: torch.Tensor, idx: torch.Tensor, weights: torc
     code = _dtype_code(grad_pts)
     out = torch.empty((n_vox, c), dtype=grad_pts.dtype, device=grad_pts.device)
     acc = torch.empty((n_vox, c), dtype=torch.float32, device=grad_pts.device) if code == F16 else None
+    vec = 8 if code == F16 else 4
+    if order is not None and c % vec == 0 and c // vec <= 128 and grad_pts.data_ptr() % 16 == 0:
+        check(_lib.lib().b2s_devoxelize_bwd_sorted(code, grad_pts.data_ptr(), order.data_ptr(), idx.data_ptr(),
+                                                   weights.data_ptr(), n_pts, n_vox, c, out.data_ptr(), _ptr(acc),
+                                                   _stream()), "devoxelize_bwd_sorted")
+        return out
     check(_lib.lib().b2s_devoxelize_bwd(code, grad_pts.data_ptr(), idx.data_ptr(), weights.data_ptr(),
                                         n_pts, n_vox, c, out.data_ptr(), _ptr(acc), _stream()),
           "devoxelize_bwd")
@@ -501,6 +533,59 @@ def bn_forward(x: torch.Tensor, residual: Optional[torch.Tensor], gamma, beta, r
                                          _stream()),
           "bn_forward", launches=2 if ready else 3)
     return y, stat[0], stat[1]
+
+
+def bn_stats(x: torch.Tensor, extra: int = 0) -> torch.Tensor:
+    """fp64 [2*c + extra]: per-channel sum and sum of squares of the rows of x (b2s_bn_stats)."""
+    _cuda(x)
+    x = x.contiguous()
+    n, c = x.shape
+    sums = torch.zeros(2 * c + extra, dtype=torch.float64, device=x.device)
+    check(_lib.lib().b2s_bn_stats(_dtype_code(x), x.data_ptr(), n, c, sums.data_ptr(), _stream()), "bn_stats", launches=1)
+    return sums
+
+
+def bn_forward_global(x, residual, gamma, beta, running_mean, running_var, eps, momentum, relu, sums_count):
+    """bn_forward from ALL-REDUCED statistics: ``sums_count`` fp64 [2c + 1] = global sums and the global row count."""
+    _cuda(x, residual)
+    x = x.contiguous()
+    if residual is not None:
+        residual = residual.contiguous()
+    n, c = x.shape
+    y = torch.empty_like(x)
+    stat = torch.empty((4, c), dtype=torch.float32, device=x.device)
+    check(_lib.lib().b2s_bn_forward_sums(_dtype_code(x), x.data_ptr(), _ptr(residual), n, c, _ptr(gamma),
+                                         _ptr(beta), float(eps), float(momentum), _ptr(running_mean),
+                                         _ptr(running_var), int(relu), y.data_ptr(), stat[0].data_ptr(),
+                                         stat[1].data_ptr(), stat[2].data_ptr(), sums_count.data_ptr(), 2,
+                                         _stream()), "bn_forward", launches=2)
+    return y, stat[0], stat[1]
+
+
+def bn_backward_reduce(dy, y, x, mean, invstd, relu: bool) -> torch.Tensor:
+    """fp64 [2, c] = (sum dy', sum dy' * xhat) over the local rows (dy' = dy masked by the ReLU)."""
+    _cuda(dy, y, x)
+    dy = dy.contiguous()
+    n, c = x.shape
+    sums = torch.empty((2, c), dtype=torch.float64, device=x.device)
+    check(_lib.lib().b2s_bn_backward_reduce(_dtype_code(x), dy.data_ptr(), _ptr(y), x.data_ptr(), n, c,
+                                            mean.data_ptr(), invstd.data_ptr(), int(relu), sums.data_ptr(),
+                                            _stream()), "bn_backward_reduce")
+    return sums
+
+
+def bn_backward_apply(dy, y, x, mean, invstd, gamma, relu: bool, want_dres: bool, sums, n_total):
+    """(dx, dres | None) from (all-reduced) ``sums`` and the global row count ``n_total`` (device fp64 [1])."""
+    _cuda(dy, y, x)
+    dy = dy.contiguous()
+    n, c = x.shape
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_dres else None
+    check(_lib.lib().b2s_bn_backward_apply(_dtype_code(x), dy.data_ptr(), _ptr(y), x.data_ptr(), n, c,
+                                           mean.data_ptr(), invstd.data_ptr(), _ptr(gamma), int(relu),
+                                           dx.data_ptr(), _ptr(dres), sums.data_ptr(), _ptr(n_total), _stream()),
+          "bn_backward_apply")
+    return dx, dres
 
 
 def bn_backward(dy: torch.Tensor, y: Optional[torch.Tensor], x: torch.Tensor, mean, invstd, gamma,

@@ -91,7 +91,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const T* __restric
 
 // mean / invstd / scale / shift from the sums; running statistics like nn.BatchNorm1d
 // (momentum update with the unbiased variance).
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t n, int c,
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t n_host, const double* __restrict__ n_dev,
+                                   int c,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float eps, float momentum, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float* __restrict__ mean_out,
@@ -99,7 +100,9 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t n, i
                                    float* __restrict__ shift) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
-  const double inv_n = 1.0 / (double)n;
+  // n_dev: the (all-reduced) global row count of synchronised batch norm, else the local row count
+  const double n = n_dev ? *n_dev : (double)n_host;
+  const double inv_n = 1.0 / n;
   const double m = sums[ch] * inv_n;
   double var = sums[c + ch] * inv_n - m * m;
   if (var < 0.0) var = 0.0;
@@ -110,7 +113,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t n, i
   scale[ch] = g * invstd;
   shift[ch] = b - (float)m * g * invstd;
   if (running_mean) {
-    const double unbiased = n > 1 ? var * (double)n / (double)(n - 1) : var;
+    const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
     running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)m;
     running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
   }
@@ -211,7 +214,8 @@ template <typename T>
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
     const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ x, int64_t n, int c,
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-    const double* __restrict__ sums, int relu, T* __restrict__ dx, T* __restrict__ dres) {
+    const double* __restrict__ sums, const double* __restrict__ n_dev, int relu, T* __restrict__ dx,
+    T* __restrict__ dres) {
   constexpr int W = VecT<T>::W;
   const int groups = c / W;
   const int cg = threadIdx.x % groups;
@@ -219,7 +223,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
   const int rl = threadIdx.x / groups;
   if (rl >= rows_per_block) return;
   float m[W], is[W], k0[W], k1[W], k2[W];
-  const float inv_n = 1.f / (float)n;
+  const float inv_n = n_dev ? (float)(1.0 / *n_dev) : 1.f / (float)n;   // sums are global under sync BN
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     const int ch = cg * W + j;
@@ -302,7 +306,8 @@ int b2s_bn_forward_sums(int32_t dtype, const void* x, const void* residual, int6
     else
       bn_stats_kernel<float><<<grid, kBnThreads, sh, st>>>(reinterpret_cast<const float*>(x), n, c, sums);
   }
-  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(sums, n, c, gamma, beta, eps, momentum, running_mean,
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(sums, n, sums_ready == 2 ? sums + 2 * c : nullptr, c, gamma,
+                                                      beta, eps, momentum, running_mean,
                                                       running_var, mean, invstd, scale_shift,
                                                       scale_shift + c);
   if (dtype == B2S_F16)
@@ -317,38 +322,75 @@ int b2s_bn_forward_sums(int32_t dtype, const void* x, const void* residual, int6
   return B2S_OK;
 }
 
+int b2s_bn_stats(int32_t dtype, const void* x, int64_t n, int32_t c, double* sums, b2s_stream_t stream) {
+  B2S_REQUIRE((dtype == B2S_F32 || dtype == B2S_F16) && n >= 1 && c >= 1 && x && sums, B2S_ERR_INVALID,
+              "b2s_bn_stats: bad argument");
+  B2S_REQUIRE(bn_shape_ok(dtype, c), B2S_ERR_UNSUPPORTED, "b2s_bn_stats: C=%d not a vector multiple", c);
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(sums, 0, 2 * c * sizeof(double), st);
+  const int grid = bn_grid(n, c, dtype == B2S_F16 ? 8 : 4);
+  const size_t sh = 2 * c * sizeof(float);
+  if (dtype == B2S_F16)
+    bn_stats_kernel<__half><<<grid, kBnThreads, sh, st>>>(reinterpret_cast<const __half*>(x), n, c, sums);
+  else
+    bn_stats_kernel<float><<<grid, kBnThreads, sh, st>>>(reinterpret_cast<const float*>(x), n, c, sums);
+  B2S_CHECK_LAUNCH("b2s_bn_stats");
+  return B2S_OK;
+}
+
+int b2s_bn_backward_reduce(int32_t dtype, const void* dy, const void* y, const void* x, int64_t n, int32_t c,
+                           const float* mean, const float* invstd, int32_t relu, double* sums,
+                           b2s_stream_t stream) {
+  B2S_REQUIRE(dtype == B2S_F32 || dtype == B2S_F16, B2S_ERR_INVALID, "b2s_bn_backward: dtype");
+  B2S_REQUIRE(n >= 1 && c >= 1 && dy && x && mean && invstd && sums && (!relu || y), B2S_ERR_INVALID,
+              "b2s_bn_backward: bad argument");
+  B2S_REQUIRE(bn_shape_ok(dtype, c), B2S_ERR_UNSUPPORTED, "b2s_bn_backward: C=%d not a vector multiple", c);
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(sums, 0, 2 * c * sizeof(double), st);
+  const int grid = bn_grid(n, c, dtype == B2S_F16 ? 8 : 4);
+  const size_t sh = 2 * c * sizeof(float);
+  if (dtype == B2S_F16)
+    bn_bwd_reduce_kernel<__half><<<grid, kBnThreads, sh, st>>>(
+        reinterpret_cast<const __half*>(dy), reinterpret_cast<const __half*>(y),
+        reinterpret_cast<const __half*>(x), n, c, mean, invstd, relu, sums);
+  else
+    bn_bwd_reduce_kernel<float><<<grid, kBnThreads, sh, st>>>(
+        reinterpret_cast<const float*>(dy), reinterpret_cast<const float*>(y),
+        reinterpret_cast<const float*>(x), n, c, mean, invstd, relu, sums);
+  B2S_CHECK_LAUNCH("b2s_bn_backward_reduce");
+  return B2S_OK;
+}
+
+int b2s_bn_backward_apply(int32_t dtype, const void* dy, const void* y, const void* x, int64_t n, int32_t c,
+                          const float* mean, const float* invstd, const float* gamma, int32_t relu, void* dx,
+                          void* dres, const double* sums, const double* n_total, b2s_stream_t stream) {
+  B2S_REQUIRE(dtype == B2S_F32 || dtype == B2S_F16, B2S_ERR_INVALID, "b2s_bn_backward: dtype");
+  B2S_REQUIRE(n >= 1 && c >= 1 && dy && x && dx && mean && invstd && sums && (!relu || y), B2S_ERR_INVALID,
+              "b2s_bn_backward: bad argument");
+  B2S_REQUIRE(bn_shape_ok(dtype, c), B2S_ERR_UNSUPPORTED, "b2s_bn_backward: C=%d not a vector multiple", c);
+  cudaStream_t st = as_stream(stream);
+  const int grid = bn_grid(n, c, dtype == B2S_F16 ? 8 : 4);
+  if (dtype == B2S_F16)
+    bn_bwd_apply_kernel<__half><<<grid, kBnThreads, 0, st>>>(
+        reinterpret_cast<const __half*>(dy), reinterpret_cast<const __half*>(y),
+        reinterpret_cast<const __half*>(x), n, c, mean, invstd, gamma, sums, n_total, relu,
+        reinterpret_cast<__half*>(dx), reinterpret_cast<__half*>(dres));
+  else
+    bn_bwd_apply_kernel<float><<<grid, kBnThreads, 0, st>>>(
+        reinterpret_cast<const float*>(dy), reinterpret_cast<const float*>(y),
+        reinterpret_cast<const float*>(x), n, c, mean, invstd, gamma, sums, n_total, relu,
+        reinterpret_cast<float*>(dx), reinterpret_cast<float*>(dres));
+  B2S_CHECK_LAUNCH("b2s_bn_backward_apply");
+  return B2S_OK;
+}
+
 int b2s_bn_backward(int32_t dtype, const void* dy, const void* y, const void* x, int64_t n, int32_t c,
                     const float* mean, const float* invstd, const float* gamma, int32_t relu, void* dx,
                     void* dres, double* sums /*[2][c]: d_beta, d_gamma on return*/,
                     b2s_stream_t stream) {
-  B2S_REQUIRE(dtype == B2S_F32 || dtype == B2S_F16, B2S_ERR_INVALID, "b2s_bn_backward: dtype");
-  B2S_REQUIRE(n >= 1 && c >= 1 && dy && x && dx && mean && invstd && sums && (!relu || y),
-              B2S_ERR_INVALID, "b2s_bn_backward: bad argument");
-  B2S_REQUIRE(bn_shape_ok(dtype, c), B2S_ERR_UNSUPPORTED, "b2s_bn_backward: C=%d not a vector multiple", c);
-  cudaStream_t st = as_stream(stream);
-  cudaMemsetAsync(sums, 0, 2 * c * sizeof(double), st);
-  const int w = dtype == B2S_F16 ? 8 : 4;
-  const int grid = bn_grid(n, c, w);
-  const size_t sh = 2 * c * sizeof(float);
-  if (dtype == B2S_F16) {
-    bn_bwd_reduce_kernel<__half><<<grid, kBnThreads, sh, st>>>(
-        reinterpret_cast<const __half*>(dy), reinterpret_cast<const __half*>(y),
-        reinterpret_cast<const __half*>(x), n, c, mean, invstd, relu, sums);
-    bn_bwd_apply_kernel<__half><<<grid, kBnThreads, 0, st>>>(
-        reinterpret_cast<const __half*>(dy), reinterpret_cast<const __half*>(y),
-        reinterpret_cast<const __half*>(x), n, c, mean, invstd, gamma, sums, relu,
-        reinterpret_cast<__half*>(dx), reinterpret_cast<__half*>(dres));
-  } else {
-    bn_bwd_reduce_kernel<float><<<grid, kBnThreads, sh, st>>>(
-        reinterpret_cast<const float*>(dy), reinterpret_cast<const float*>(y),
-        reinterpret_cast<const float*>(x), n, c, mean, invstd, relu, sums);
-    bn_bwd_apply_kernel<float><<<grid, kBnThreads, 0, st>>>(
-        reinterpret_cast<const float*>(dy), reinterpret_cast<const float*>(y),
-        reinterpret_cast<const float*>(x), n, c, mean, invstd, gamma, sums, relu,
-        reinterpret_cast<float*>(dx), reinterpret_cast<float*>(dres));
-  }
-  B2S_CHECK_LAUNCH("b2s_bn_backward");
-  return B2S_OK;
+  int rc = b2s_bn_backward_reduce(dtype, dy, y, x, n, c, mean, invstd, relu, sums, stream);
+  if (rc != B2S_OK) return rc;
+  return b2s_bn_backward_apply(dtype, dy, y, x, n, c, mean, invstd, gamma, relu, dx, dres, sums, nullptr, stream);
 }
 
 }  // extern "C"

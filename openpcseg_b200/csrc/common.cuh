@@ -35,6 +35,10 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 // Number of SMs of the current device (cached).  Grid sizes for the grid-stride
 // kernels are multiples of it.
 int sm_count();
+// SMs the persistent (one CTA per SM slot) kernels fill: sm_count() minus the reserve set by
+// b2s_set_sm_reserve / B2S_SM_RESERVE (room for concurrent collectives)
+int persistent_sms();
+void set_sm_reserve(int n);
 
 constexpr int64_t kEmptyKey = -1;  // reserved table key (memset 0xFF); sphash values are < 2^60
 

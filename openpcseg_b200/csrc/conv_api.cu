@@ -26,7 +26,7 @@ void launch_weight_to_kmajor(const void* w, int k, int c_in, int c_out, void* ou
 int tc4_tile_rows(int c_res, int64_t n_rows);
 bool tc_wgrad_supported(int c_in, int c_out);
 int launch_wgrad_tc(const void* in, int64_t n_in, const void* gout, int64_t n_out, const int32_t* nbmaps,
-                    const int32_t* nbsizes, int64_t n_identity, int64_t n_pairs_bound, int k,
+                    const int32_t* nbsizes, int n_seg, int64_t n_identity, int64_t n_pairs_bound, int k,
                     int c_in, int c_out, int swap_pairs, float* gw, cudaStream_t st);
 
 static bool force_simt() {
@@ -127,6 +127,14 @@ int b2s_conv_wgrad(int32_t dtype, const void* in, int64_t n_in, const void* grad
                    size_t ws_bytes, b2s_stream_t stream) {
   (void)ws;
   (void)ws_bytes;
+  return b2s_conv_wgrad_segments(dtype, in, n_in, grad_out, n_out, k, c_in, c_out, nbmaps, nbsizes, k, swap_pairs,
+                                 grad_w, stream);
+}
+
+int b2s_conv_wgrad_segments(int32_t dtype, const void* in, int64_t n_in, const void* grad_out,
+                            int64_t n_out, int32_t k, int32_t c_in, int32_t c_out, const int32_t* nbmaps,
+                            const int32_t* nbsizes, int32_t n_seg, int32_t swap_pairs, float* grad_w,
+                            b2s_stream_t stream) {
   B2S_REQUIRE(dtype == B2S_F32 || dtype == B2S_F16, B2S_ERR_INVALID, "b2s_conv_wgrad: dtype");
   B2S_REQUIRE(k >= 1 && c_in >= 1 && c_out >= 1 && n_in >= 0 && n_out >= 0 && grad_w,
               B2S_ERR_INVALID, "b2s_conv_wgrad: bad argument");
@@ -143,10 +151,15 @@ int b2s_conv_wgrad(int32_t dtype, const void* in, int64_t n_in, const void* grad
   // the tensor-core kernel addresses rows by 32-bit byte offsets
   const bool small = n_in * (int64_t)c_in * 2 < 0xFFFFFF00LL && n_out * (int64_t)c_out * 2 < 0xFFFFFF00LL;
   if (dtype == B2S_F16 && !force_simt() && small && tc_wgrad_supported(c_in, c_out)) {
-    int rc = launch_wgrad_tc(in, n_in, grad_out, n_out, nbmaps, nbsizes, n_identity, bound, k, c_in, c_out,
-                             swap_pairs, grad_w, st);
+    int rc = launch_wgrad_tc(in, n_in, grad_out, n_out, nbmaps, nbsizes, nbmaps ? n_seg : k, n_identity, bound, k,
+                             c_in, c_out, swap_pairs, grad_w, st);
     if (rc != B2S_OK) return rc;
-  } else if (dtype == B2S_F16) {
+    B2S_CHECK_LAUNCH("b2s_conv_wgrad");
+    return B2S_OK;
+  }
+  B2S_REQUIRE(n_seg == k, B2S_ERR_UNSUPPORTED,
+              "b2s_conv_wgrad_segments: segmented pair lists need the tensor-core kernel");
+  if (dtype == B2S_F16) {
     launch_wgrad_simt<__half>(in, grad_out, nbmaps, nbsizes, n_identity, bound, k, c_in, c_out,
                               swap_pairs, grad_w, st);
   } else {

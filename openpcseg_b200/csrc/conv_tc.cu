@@ -142,10 +142,10 @@ struct WParams {
   const __half* x;        // [n_in, c_in]
   const __half* gy;       // [n_out, c_out]
   const int32_t* pairs;   // [M, 2] (in, out) or nullptr (identity)
-  const int32_t* nbsizes; // [K] or nullptr
+  const int32_t* nbsizes; // [n_seg] segment sizes (n_seg == K: the per-offset counts) or nullptr
   float* gw;              // [K, c_in, c_out]
   int64_t n_identity;
-  int kvol, c_in, c_out, swap_pairs;
+  int kvol, n_seg, c_in, c_out, swap_pairs;
   int m_tiles, unit_pairs, stages, tmem_cols;
   int dbg;                // ablation: bit0 no gathers, bit1 no MMAs, bit2 no epilogue reds
 };
@@ -175,8 +175,8 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p, con
   __shared__ __align__(8) uint64_t s_empty[8];
   __shared__ __align__(8) uint64_t s_acc;
   __shared__ uint32_t s_tmem;
-  __shared__ int64_t s_start[130];         // exclusive prefix of nbsizes
-  __shared__ int s_units[130];             // exclusive prefix of units per offset
+  __shared__ int32_t s_start[1025];        // exclusive prefix of the segment sizes (nbsizes when n_seg == K)
+  __shared__ int32_t s_units[1025];        // exclusive prefix of units per segment
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = p.stages;
@@ -187,24 +187,45 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p, con
     }
     mbar_init(smem_u32(&s_acc), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    int64_t acc = 0;
-    int u = 0;
-    for (int k = 0; k < p.kvol; ++k) {
-      s_start[k] = acc;
-      s_units[k] = u;
-      int64_t cnt = p.pairs ? (int64_t)__ldg(p.nbsizes + k) : p.n_identity;
-      acc += cnt;
-      u += (int)((cnt + p.unit_pairs - 1) / p.unit_pairs);
+  }
+  if (warp == 0) {
+    // exclusive prefixes over the n_seg segments: every lane sums a contiguous run, one warp scan joins them
+    const int per = (p.n_seg + 31) / 32;
+    const int s0 = lane * per, s1 = s0 + per < p.n_seg ? s0 + per : p.n_seg;
+    int my_pairs = 0, my_units = 0;
+    for (int sgm = s0; sgm < s1; ++sgm) {
+      const int cnt = p.pairs ? __ldg(p.nbsizes + sgm) : (int)p.n_identity;
+      my_pairs += cnt;
+      my_units += (cnt + p.unit_pairs - 1) / p.unit_pairs;
     }
-    s_start[p.kvol] = acc;
-    s_units[p.kvol] = u;
+    int inc_p = my_pairs, inc_u = my_units;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int tp = __shfl_up_sync(0xffffffffu, inc_p, d), tu = __shfl_up_sync(0xffffffffu, inc_u, d);
+      if (lane >= d) {
+        inc_p += tp;
+        inc_u += tu;
+      }
+    }
+    int acc = inc_p - my_pairs, u = inc_u - my_units;
+    for (int sgm = s0; sgm < s1; ++sgm) {
+      s_start[sgm] = acc;
+      s_units[sgm] = u;
+      const int cnt = p.pairs ? __ldg(p.nbsizes + sgm) : (int)p.n_identity;
+      acc += cnt;
+      u += (cnt + p.unit_pairs - 1) / p.unit_pairs;
+    }
+    if (lane == 31) {
+      s_start[p.n_seg] = inc_p;
+      s_units[p.n_seg] = inc_u;
+    }
   }
   if (warp == 4) tmem_alloc(smem_u32(&s_tmem), (uint32_t)p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = s_tmem;
-  const int total_units = s_units[p.kvol] * p.m_tiles;
+  const int total_units = s_units[p.n_seg] * p.m_tiles;
   // C_out > 256: two MMAs per K step, N = 256 and N = C_out - 256 (the B operand of the second one starts
   // at the fifth 64-channel panel, so any C_out % 16 == 0 up to 512 works, e.g. 448 of RPVNet cr1.75)
   const int n_first = p.c_out > 256 ? 256 : p.c_out;
@@ -215,10 +236,14 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p, con
   for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x, ++unit_no) {
     const int mt = unit % p.m_tiles;
     const int ku = unit / p.m_tiles;
-    int k = 0;
-    while (s_units[k + 1] <= ku) ++k;
-    const int64_t cnt_k = s_start[k + 1] - s_start[k];
-    const int64_t lo = (int64_t)(ku - s_units[k]) * p.unit_pairs;
+    int sg = 0;                                                     // segment of this unit: last s_units[sg] <= ku
+    for (int hi_s = p.n_seg; hi_s - sg > 1;) {
+      const int mid = (sg + hi_s) >> 1;
+      if (s_units[mid] <= ku) sg = mid; else hi_s = mid;
+    }
+    const int k = sg % p.kvol;                                      // the offset the segment belongs to
+    const int64_t cnt_k = s_start[sg + 1] - s_start[sg];
+    const int64_t lo = (int64_t)(ku - s_units[sg]) * p.unit_pairs;
     const int64_t hi = lo + p.unit_pairs < cnt_k ? lo + p.unit_pairs : cnt_k;
     const int n_stage = (int)((hi - lo + kRows - 1) / kRows);
     const int ch_base = mt * 128;                                   // first c_in channel of the slab
@@ -227,7 +252,7 @@ __global__ void __launch_bounds__(kThreads) wgrad_tc_kernel(const WParams p, con
       // ---------------------------------------------------------------- producers
       const int sub = lane >> 3, chunk = lane & 7;
       const int2* pr = reinterpret_cast<const int2*>(p.pairs);
-      const int64_t pair0 = s_start[k];
+      const int64_t pair0 = s_start[sg];
       // Rows are addressed by 32-bit byte offsets from x / gy (the dispatcher keeps tensors of 4 GiB
       // and more on the SIMT kernel): one multiply per pair instead of 64-bit address arithmetic per
       // 16-byte copy, which made these warps latency-bound on their own instruction stream.
@@ -404,10 +429,11 @@ static cudaError_t launch_wgrad_variant(const WParams& p, const CUtensorMap& tmx
 }  // namespace tcw
 
 int launch_wgrad_tc(const void* in, int64_t n_in, const void* gout, int64_t n_out, const int32_t* nbmaps,
-                    const int32_t* nbsizes, int64_t n_identity, int64_t n_pairs_bound, int k,
+                    const int32_t* nbsizes, int n_seg, int64_t n_identity, int64_t n_pairs_bound, int k,
                     int c_in, int c_out, int swap_pairs, float* gw, cudaStream_t st) {
   using namespace tcw;
-  B2S_REQUIRE(k <= 128, B2S_ERR_UNSUPPORTED, "b2s_conv_wgrad: kernel volume %d > 128", k);
+  B2S_REQUIRE(k <= 128 && n_seg >= 1 && n_seg <= 1024 && n_seg % k == 0, B2S_ERR_UNSUPPORTED,
+              "b2s_conv_wgrad: kernel volume %d > 128 or %d segments", k, n_seg);
   WParams p;
   p.x = reinterpret_cast<const __half*>(in);
   p.gy = reinterpret_cast<const __half*>(gout);
@@ -416,6 +442,7 @@ int launch_wgrad_tc(const void* in, int64_t n_in, const void* gout, int64_t n_ou
   p.gw = gw;
   p.n_identity = n_identity;
   p.kvol = k;
+  p.n_seg = n_seg;
   p.c_in = c_in;
   p.c_out = c_out;
   p.swap_pairs = swap_pairs;
@@ -427,9 +454,10 @@ int launch_wgrad_tc(const void* in, int64_t n_in, const void* gout, int64_t n_ou
   }
   p.tmem_cols = tc::tmem_cols_for(c_out);
   const int stage = (2 + (c_out + 63) / 64) * kPanelBytes;
-  int stages = (int)((110 * 1024) / stage);          // two CTAs per SM when >= 3 stages fit twice
+  // 228 KiB per SM, 1 KiB reserved per CTA, ~8.5 KiB static (segment prefixes + barriers), 1 KiB alignment slack
+  int stages = (int)((103 * 1024) / stage);          // two CTAs per SM when >= 3 stages fit twice
   const bool two_per_sm = stages >= 3 && p.tmem_cols <= 256;
-  if (!two_per_sm) stages = (int)((220 * 1024) / stage);
+  if (!two_per_sm) stages = (int)((214 * 1024) / stage);
   if (stages > 6) stages = 6;
   B2S_REQUIRE(stages >= 2, B2S_ERR_UNSUPPORTED, "b2s_conv_wgrad: tile does not fit (C_out=%d)", c_out);
   p.stages = stages;
@@ -437,7 +465,7 @@ int launch_wgrad_tc(const void* in, int64_t n_in, const void* gout, int64_t n_ou
   // per-offset pair counts differ by 10x (the centre offset has N pairs, corner offsets ~N/20);
   // at least 16 stages per unit so the fp32 reds of the epilogue stay a few % of the gathered bytes.
   // (the true pair count lives on the device; on LiDAR surfaces ~1/4 of the K*N slots exist)
-  const int sms = sm_count();
+  const int sms = persistent_sms();
   const int64_t est = k > 1 ? n_pairs_bound / 4 + 1 : n_pairs_bound;
   const int64_t slots_est = (int64_t)sms * (two_per_sm ? 2 : 1);
   int64_t per = est / (slots_est * 5) + 1;
@@ -446,7 +474,7 @@ int launch_wgrad_tc(const void* in, int64_t n_in, const void* gout, int64_t n_ou
   if (unit > 256 * kRows) unit = 256 * kRows;
   p.unit_pairs = (int)unit;
   const size_t smem = (size_t)stages * stage + 1024;
-  int64_t max_units = (n_pairs_bound / unit + k) * p.m_tiles;
+  int64_t max_units = (n_pairs_bound / unit + n_seg) * p.m_tiles;
   const int64_t slots = (int64_t)sms * (two_per_sm ? 2 : 1);
   int grid = (int)(max_units < slots ? (max_units < 1 ? 1 : max_units) : slots);
   // Both operands fetched by the TMA unit (tile::gather4) where it measured faster than cp.async

@@ -645,7 +645,7 @@ int launch_gather_gemm_tc4(const void* in, int64_t n_src, const void* wt, int k,
   B2S_REQUIRE(stages >= 2, B2S_ERR_UNSUPPORTED, "b2s_conv_gather_gemm: tile does not fit (C=%d)", c_res);
   p.stages = stages;
   const size_t smem = (size_t)stages * p.stage_stride + 1024;
-  int grid = sm_count() * ctas_per_sm;
+  int grid = persistent_sms() * ctas_per_sm;
   if (grid > p.n_tiles) grid = p.n_tiles;
   cudaError_t e = T == 2 ? launch_variant<2>(p, tm64, tm32, grid, smem, st)
                          : launch_variant<1>(p, tm64, tm32, grid, smem, st);

@@ -343,6 +343,42 @@ struct PairValid {
 };
 using PairIter = cub::TransformInputIterator<int2, PairOf, cub::CountingInputIterator<int>>;
 
+// Pairs in (chunk of launch rows, offset, launch row) order for the weight-gradient kernel: flat index
+// g = (chunk * K + k) * chunk_rows + j'  ->  launch row j = chunk * chunk_rows + j', map column perm[j] (or j).
+struct ChunkPairOf {
+  const int32_t* nbr;
+  const int32_t* perm;
+  int32_t n, k, chunk_rows;
+  __host__ __device__ __forceinline__ int2 operator()(int64_t g) const {
+    const int64_t per_chunk = (int64_t)k * chunk_rows;
+    const int64_t chunk = g / per_chunk, rem = g - chunk * per_chunk;
+    const int kk = (int)(rem / chunk_rows);
+    const int64_t j = chunk * chunk_rows + (rem - (int64_t)kk * chunk_rows);
+    if (j >= n) return make_int2(-1, -1);
+    const int32_t o = perm ? perm[j] : (int32_t)j;
+    return make_int2(nbr[(int64_t)kk * n + o], o);
+  }
+};
+using ChunkPairIter = cub::TransformInputIterator<int2, ChunkPairOf, cub::CountingInputIterator<int64_t>>;
+
+// seg_sizes[chunk * K + k] = number of pairs of offset k whose launch row falls into the chunk
+__global__ void __launch_bounds__(256) chunk_pair_count_kernel(const int32_t* __restrict__ nbr,
+                                                                const int32_t* __restrict__ perm, int kvol,
+                                                                int64_t n, int chunk_rows,
+                                                                int32_t* __restrict__ seg_sizes) {
+  const int64_t n_round = (n + 31) / 32 * 32;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n_round; j += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = j < n ? (perm ? (int64_t)__ldg(perm + j) : j) : -1;
+    const int chunk = (int)(j / chunk_rows);
+    // chunk_rows is a multiple of 32, so a warp's rows share the chunk
+    for (int k = 0; k < kvol; ++k) {
+      const bool have = o >= 0 && __ldg(nbr + (int64_t)k * n + o) >= 0;
+      const unsigned b = __ballot_sync(0xffffffffu, have);
+      if ((threadIdx.x & 31) == 0 && b) atomicAdd(seg_sizes + chunk * kvol + k, __popc(b));
+    }
+  }
+}
+
 static size_t sort_temp_bytes(int64_t n) {
   size_t b = 0;
   cub::DeviceRadixSort::SortKeys((void*)nullptr, b, (const uint64_t*)nullptr, (uint64_t*)nullptr,
@@ -607,6 +643,41 @@ int b2s_kmap_pairs(const int32_t* nbr_out, int32_t k, int64_t n_out, int32_t* nb
   cub::DeviceSelect::If(ws, need, it, reinterpret_cast<int2*>(nbmaps), d_total, (int)total,
                         PairValid(), st);
   B2S_CHECK_LAUNCH("b2s_kmap_pairs");
+  return B2S_OK;
+}
+
+size_t b2s_kmap_pairs_chunked_workspace_bytes(int64_t n_out, int32_t k, int32_t n_chunks) {
+  const int64_t chunk_rows = ((ceil_div(n_out < 1 ? 1 : n_out, (int64_t)(n_chunks < 1 ? 1 : n_chunks)) + 31) / 32) * 32;
+  const int64_t total = chunk_rows * (int64_t)(n_chunks < 1 ? 1 : n_chunks) * (k < 1 ? 1 : k);
+  size_t need = 0;
+  ChunkPairIter it(cub::CountingInputIterator<int64_t>(0), ChunkPairOf{nullptr, nullptr, 1, 1, 32});
+  cub::DeviceSelect::If((void*)nullptr, need, it, (int2*)nullptr, (int64_t*)nullptr, total, PairValid());
+  return align_up(need, 256);
+}
+
+int b2s_kmap_pairs_chunked(const int32_t* nbr_out, int32_t k, int64_t n_out, const int32_t* perm,
+                           int32_t n_chunks, int32_t* nbmaps, int32_t* seg_sizes, int64_t* d_total, void* ws,
+                           size_t ws_bytes, b2s_stream_t stream) {
+  B2S_REQUIRE(k >= 1 && n_out >= 0 && n_chunks >= 1 && d_total && seg_sizes, B2S_ERR_INVALID,
+              "b2s_kmap_pairs_chunked: bad argument");
+  cudaStream_t st = as_stream(stream);
+  cudaMemsetAsync(seg_sizes, 0, (size_t)n_chunks * k * sizeof(int32_t), st);
+  if (n_out == 0) {
+    cudaMemsetAsync(d_total, 0, sizeof(int64_t), st);
+    return B2S_OK;
+  }
+  B2S_REQUIRE(nbr_out && nbmaps && ws, B2S_ERR_INVALID, "b2s_kmap_pairs_chunked: null pointer");
+  B2S_REQUIRE(n_out * (int64_t)k < (1LL << 31), B2S_ERR_UNSUPPORTED, "b2s_kmap_pairs_chunked: K*N >= 2^31");
+  const int64_t chunk_rows = ((ceil_div(n_out, (int64_t)n_chunks) + 31) / 32) * 32;
+  const int64_t total = chunk_rows * (int64_t)n_chunks * k;
+  chunk_pair_count_kernel<<<grid_for(n_out, 256), 256, 0, st>>>(nbr_out, perm, k, n_out, (int)chunk_rows, seg_sizes);
+  ChunkPairIter it(cub::CountingInputIterator<int64_t>(0),
+                   ChunkPairOf{nbr_out, perm, (int32_t)n_out, k, (int32_t)chunk_rows});
+  size_t need = 0;
+  cub::DeviceSelect::If((void*)nullptr, need, it, (int2*)nullptr, (int64_t*)nullptr, total, PairValid());
+  B2S_REQUIRE(ws_bytes >= need, B2S_ERR_WORKSPACE, "b2s_kmap_pairs_chunked: workspace needs %zu bytes", need);
+  cub::DeviceSelect::If(ws, need, it, reinterpret_cast<int2*>(nbmaps), d_total, total, PairValid(), st);
+  B2S_CHECK_LAUNCH("b2s_kmap_pairs_chunked");
   return B2S_OK;
 }
 

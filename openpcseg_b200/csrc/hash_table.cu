@@ -5,6 +5,8 @@
 // sector per probe.  One int4 (16 B) coordinate load per thread, one 8 B store.
 #include <stdarg.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b2s {
@@ -29,6 +31,20 @@ int sm_count() {
   }
   return cached;
 }
+
+// SMs the persistent kernels (conv gather-GEMM, wgrad) may fill: all but `reserve`, so that a concurrent
+// collective (NCCL's gradient all-reduce under DDP) finds free SMs instead of queueing behind a resident grid
+static int g_sm_reserve = -1;
+int persistent_sms() {
+  if (g_sm_reserve < 0) {
+    const char* e = getenv("B2S_SM_RESERVE");
+    g_sm_reserve = e ? atoi(e) : 0;
+    if (g_sm_reserve < 0) g_sm_reserve = 0;
+  }
+  const int n = sm_count() - g_sm_reserve;
+  return n < 8 ? 8 : n;
+}
+void set_sm_reserve(int n) { g_sm_reserve = n < 0 ? 0 : n; }
 
 __global__ void __launch_bounds__(256) hash_kernel(const int4* __restrict__ coords, int64_t n,
                                                     int64_t* __restrict__ out) {
@@ -112,7 +128,8 @@ using namespace b2s;
 extern "C" {
 
 const char* b2s_last_error(void) { return g_err; }
-int b2s_version(void) { return 100; }
+int b2s_version(void) { return 200; }
+void b2s_set_sm_reserve(int32_t n) { b2s::set_sm_reserve(n); }
 
 int b2s_hash(const int32_t* coords, int64_t n, int64_t* out, b2s_stream_t stream) {
   B2S_REQUIRE(n >= 0, B2S_ERR_INVALID, "b2s_hash: n < 0");

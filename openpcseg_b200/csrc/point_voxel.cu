@@ -180,6 +180,57 @@ __global__ void __launch_bounds__(256) devoxelize_bwd_kernel(const T* __restrict
   }
 }
 
+// The same scatter for CONTENDED maps (coarse strides: ~27 points per stride-16 voxel, every one of them adding
+// into the same 8 corner rows - the plain kernel runs at the L2 atomic rate).  Points are visited in `order`
+// (sorted by their corner-0 voxel, so neighbours in the order share all eight corners); a thread owns one
+// V-channel group, walks kPts consecutive points and keeps one running sum per corner in registers, flushing a
+// corner with a vector red only when its voxel changes: ~run-length times fewer atomics.
+template <typename T, int V, int kPts>
+__global__ void __launch_bounds__(128) devoxelize_bwd_sorted_kernel(const T* __restrict__ grad_pts,
+                                                                     const int32_t* __restrict__ order,
+                                                                     const int32_t* __restrict__ idx,
+                                                                     const float* __restrict__ w, int64_t n_pts,
+                                                                     int c, float* __restrict__ acc) {
+  const int groups = c / V;
+  const int slices = blockDim.x / groups;                   // point slices per block
+  const int cg = threadIdx.x % groups, sl = threadIdx.x / groups;
+  if (sl >= slices) return;
+  const int64_t p0 = ((int64_t)blockIdx.x * slices + sl) * kPts;
+  if (p0 >= n_pts) return;
+  const int64_t p1 = p0 + kPts < n_pts ? p0 + kPts : n_pts;
+  const int ch = cg * V;
+  float run[8][V];
+  int32_t cur[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    cur[k] = -1;
+#pragma unroll
+    for (int j = 0; j < V; ++j) run[k][j] = 0.f;
+  }
+  for (int64_t q = p0; q < p1; ++q) {
+    const int64_t p = __ldg(order + q);
+    Vec<T, V> g;
+    g.load(grad_pts + p * c + ch);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int32_t r = __ldg(idx + p * 8 + k);
+      const float wk = r >= 0 ? __ldg(w + p * 8 + k) : 0.f;
+      if (r < 0 || wk == 0.f) continue;
+      if (r != cur[k]) {
+        if (cur[k] >= 0) red_add<V>(acc + (int64_t)cur[k] * c + ch, run[k]);
+        cur[k] = r;
+#pragma unroll
+        for (int j = 0; j < V; ++j) run[k][j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < V; ++j) run[k][j] = fmaf(wk, g.get(j), run[k][j]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (cur[k] >= 0) red_add<V>(acc + (int64_t)cur[k] * c + ch, run[k]);
+}
+
 __global__ void __launch_bounds__(256) f32_to_f16_kernel(const float* __restrict__ src, int64_t n,
                                                           __half* __restrict__ dst) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
@@ -501,6 +552,40 @@ int b2s_devoxelize_bwd(int32_t dtype, const void* grad_pts, const int32_t* idx,
     f32_to_f16_kernel<<<grid_for(n_vox * c, 256), 256, 0, st>>>(acc, n_vox * c,
                                                                 reinterpret_cast<__half*>(grad_vox));
   B2S_CHECK_LAUNCH("b2s_devoxelize_bwd");
+  return B2S_OK;
+}
+
+int b2s_devoxelize_bwd_sorted(int32_t dtype, const void* grad_pts, const int32_t* order, const int32_t* idx,
+                              const float* weights, int64_t n_pts, int64_t n_vox, int32_t c, void* grad_vox,
+                              float* acc, b2s_stream_t stream) {
+  B2S_REQUIRE(n_pts >= 0 && n_vox >= 0 && c >= 1, B2S_ERR_INVALID, "b2s_devoxelize_bwd_sorted: bad sizes");
+  B2S_REQUIRE(dtype == B2S_F32 || dtype == B2S_F16, B2S_ERR_INVALID, "b2s_devoxelize_bwd_sorted: dtype");
+  const int v = dtype == B2S_F16 ? 8 : 4;
+  B2S_REQUIRE(c % v == 0 && c / v <= 128 && aligned16(grad_pts), B2S_ERR_UNSUPPORTED,
+              "b2s_devoxelize_bwd_sorted: C=%d must be a multiple of the 16-byte vector (use b2s_devoxelize_bwd)", c);
+  if (n_vox == 0) return B2S_OK;
+  B2S_REQUIRE(grad_vox && (dtype == B2S_F32 || acc), B2S_ERR_INVALID,
+              "b2s_devoxelize_bwd_sorted: null pointer (fp16 needs the fp32 scratch)");
+  cudaStream_t st = as_stream(stream);
+  float* target = dtype == B2S_F32 ? reinterpret_cast<float*>(grad_vox) : acc;
+  cudaMemsetAsync(target, 0, (size_t)n_vox * c * sizeof(float), st);
+  if (n_pts > 0) {
+    B2S_REQUIRE(grad_pts && order && idx && weights, B2S_ERR_INVALID, "b2s_devoxelize_bwd_sorted: null pointer");
+    constexpr int kPts = 32;
+    const int groups = c / v;
+    const int slices = 128 / groups;
+    const unsigned grid = (unsigned)ceil_div(n_pts, (int64_t)slices * kPts);
+    if (dtype == B2S_F16)
+      devoxelize_bwd_sorted_kernel<__half, 8, kPts><<<grid, 128, 0, st>>>(
+          reinterpret_cast<const __half*>(grad_pts), order, idx, weights, n_pts, c, target);
+    else
+      devoxelize_bwd_sorted_kernel<float, 4, kPts><<<grid, 128, 0, st>>>(
+          reinterpret_cast<const float*>(grad_pts), order, idx, weights, n_pts, c, target);
+  }
+  if (dtype == B2S_F16)
+    f32_to_f16_kernel<<<grid_for(n_vox * c, 256), 256, 0, st>>>(acc, n_vox * c,
+                                                                reinterpret_cast<__half*>(grad_vox));
+  B2S_CHECK_LAUNCH("b2s_devoxelize_bwd_sorted");
   return B2S_OK;
 }
 

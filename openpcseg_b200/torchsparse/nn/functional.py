@@ -94,7 +94,18 @@ class _Devoxelize(Function):
     @once_differentiable
     def backward(ctx, grad):
         idx, weights, n_vox = ctx.aux
-        return B.devoxelize_backward(grad.contiguous(), idx, weights, n_vox), None, None
+        order = None
+        if idx.shape[0] >= 2 * n_vox and grad.is_cuda:
+            # many points per voxel (coarse strides): visit the points sorted by their corner-0 voxel so that the
+            # kernel can merge runs in registers; the order is cached on the (per-stride cached) index tensor
+            order = getattr(idx, "_b2s_order", None)
+            if order is None:
+                order = torch.argsort(idx[:, 0]).int()
+                try:
+                    idx._b2s_order = order
+                except AttributeError:
+                    pass
+        return B.devoxelize_backward(grad.contiguous(), idx, weights, n_vox, order), None, None
 
 
 def spdevoxelize(feats: torch.Tensor, coords: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
@@ -136,12 +147,28 @@ class KernelMap:
         self.tile_perm = self._row_bits = None
         self._steps = {}                # (which map, tile_rows) -> step table
         self._pairs = None              # (int32 [K*N_out, 2] padded, int64 [1] total)
+        self._chunked = None            # (pairs in (row range, offset) order, segment sizes)
         self._ref = None
 
     def pairs(self):
         if self._pairs is None:
             self._pairs = B.kmap_pairs(self.nbr_out)
         return self._pairs
+
+    def wgrad_pairs(self, feats: torch.Tensor):
+        """(pairs, sizes) for the weight gradient: the reference-order list, or (B2S_WGRAD_CHUNKED=1, experimental)
+        the list in (row range, offset) order over a spatial (batch, z, x, y) order of the rows, meant to keep one
+        range's X / dY rows in L2 across its 27 offsets (the plain list re-reads rows from HBM once per offset
+        when the level outgrows L2: ncu 416 MB read vs 160 MB algorithmic at batch 4, stride 1)."""
+        n_out = self.nbr_out.shape[1]
+        n_chunks = min(-(-n_out // _WGRAD_CHUNK_ROWS), 1024 // self.kvol)
+        if n_chunks <= 1 or feats.dtype != torch.float16 or not _WGRAD_CHUNKED:
+            return self.pairs()[0], self.nbsizes32
+        if self._chunked is None:
+            perm = _tile_order(self._coords) if (self.symmetric and self._coords is not None) else None
+            pairs, seg, _ = B.kmap_pairs_chunked(self.nbr_out, perm, n_chunks)
+            self._chunked = (pairs, seg)
+        return self._chunked
 
     def total_hint(self):
         """Device scalar with the pair count M (used by the measurement hooks only)."""
@@ -201,6 +228,11 @@ class KernelMap:
 
 
 _TILE_ORDER = os.environ.get("B2S_TILE_ORDER", "mask")      # "mask" | "zxy" | "none"
+# opt-in: measured SLOWER than the plain list (profiles/r2_wgrad_chunked.txt: stride-1 level at batch 16
+# 568 -> 701 us) - the plain (offset, ascending row) list reads dY sequentially, the range-major spatial order
+# turns both operands into scattered gathers and doubles the number of small work units
+_WGRAD_CHUNKED = os.environ.get("B2S_WGRAD_CHUNKED", "0") == "1"
+_WGRAD_CHUNK_ROWS = int(os.environ.get("B2S_WGRAD_CHUNK_ROWS", 65536))
 
 
 def _tile_order(coords: torch.Tensor) -> torch.Tensor:
@@ -324,9 +356,8 @@ class ConvolutionFunction(Function):
         if ctx.needs_input_grad[0]:
             grad_in = _conv_rows(grad_out, w, kmap, "out" if transposed else "in", True, None, hint)
         if ctx.needs_input_grad[1]:
-            pairs, _ = kmap.pairs()
-            grad_w = B.conv_wgrad(feats, grad_out, kmap.kvol, pairs, kmap.nbsizes32, transposed,
-                                  pairs_hint=hint)
+            pairs, sizes = kmap.wgrad_pairs(feats)
+            grad_w = B.conv_wgrad(feats, grad_out, kmap.kvol, pairs, sizes, transposed, pairs_hint=hint)
             grad_w = grad_w.to(weight.dtype)
         return grad_in, grad_w, None, None, None
 
@@ -468,6 +499,41 @@ class _BatchNormAct(Function):
                 dbeta.to(gamma.dtype) if gamma is not None else None, None, None, None, None, None, None)
 
 
+class _SyncBatchNormAct(Function):
+    """Synchronised (cross-rank) variant of _BatchNormAct: the same kernels with one all-reduce of the fp64
+    [2C + 1] statistics (sums + row count) in forward and one of the [2C] gradient sums in backward - instead of
+    torch.nn.SyncBatchNorm's unfused all_gather / all_reduce sequence per layer (reference: IF_DIST True,
+    minkunet.py:23-25; torch/nn/modules/_functions.py SyncBatchNorm).  Weight / bias gradients are the LOCAL
+    sums, as in torch: DistributedDataParallel averages them with the other parameters."""
+
+    @staticmethod
+    def forward(ctx, x, residual, gamma, beta, running_mean, running_var, eps, momentum, relu, group, sums=None):
+        import torch.distributed as dist
+        c = x.shape[1]
+        buf = B.bn_stats(x, extra=1) if sums is None else torch.cat([sums.reshape(-1), sums.new_zeros(1)])
+        buf[2 * c] = float(x.shape[0])
+        dist.all_reduce(buf, group=group)
+        y, mean, invstd = B.bn_forward_global(x, residual, gamma, beta, running_mean, running_var, eps, momentum,
+                                              relu, buf)
+        ctx.save_for_backward(x, y if relu else None, mean, invstd, gamma, buf[2 * c:])
+        ctx.relu, ctx.has_res, ctx.group = relu, residual is not None, group
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        import torch.distributed as dist
+        x, y, mean, invstd, gamma, n_total = ctx.saved_tensors
+        local = B.bn_backward_reduce(dy, y, x, mean, invstd, ctx.relu)
+        glob = local.clone()
+        dist.all_reduce(glob, group=ctx.group)
+        dx, dres = B.bn_backward_apply(dy, y, x, mean, invstd, gamma, ctx.relu,
+                                       ctx.has_res and ctx.needs_input_grad[1], glob, n_total)
+        dgamma = local[1].float().to(gamma.dtype) if gamma is not None else None
+        dbeta = local[0].float().to(gamma.dtype) if gamma is not None else None
+        return (dx, dres, dgamma, dbeta) + (None,) * 7
+
+
 def batch_norm_act(x: torch.Tensor, bn: torch.nn.modules.batchnorm._BatchNorm, relu: bool = False,
                    residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Fused training-mode batch norm of [N, C] rows with optional residual add and ReLU, same
@@ -475,8 +541,14 @@ def batch_norm_act(x: torch.Tensor, bn: torch.nn.modules.batchnorm._BatchNorm, r
     for SyncBatchNorm under a process group, or for channel counts the kernels do not tile."""
     sync = isinstance(bn, torch.nn.SyncBatchNorm) and torch.distributed.is_available() and \
         torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
-    if (not bn.training) or sync or not bn.track_running_stats or bn.momentum is None \
-            or not B.bn_supported(x) or (residual is not None and residual.dtype != x.dtype):
+    usable = bn.training and bn.track_running_stats and bn.momentum is not None and B.bn_supported(x) \
+        and (residual is None or residual.dtype == x.dtype)
+    if usable and sync:
+        with torch.no_grad():
+            bn.num_batches_tracked += 1
+        return _SyncBatchNormAct.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
+                                       bn.momentum, relu, bn.process_group, getattr(x, "_b2s_sums", None))
+    if not usable:
         # the dense implementation of the module's class on the [N, C] rows (the sparse wrappers'
         # own forward expects a SparseTensor)
         dense = torch.nn.SyncBatchNorm if isinstance(bn, torch.nn.SyncBatchNorm) else torch.nn.BatchNorm1d
@@ -493,7 +565,4 @@ def batch_norm_act(x: torch.Tensor, bn: torch.nn.modules.batchnorm._BatchNorm, r
 def batch_norm_fusable(x_dtype: torch.dtype, bn: torch.nn.modules.batchnorm._BatchNorm) -> bool:
     """Whether ``batch_norm_act`` will take its fused training path for this module (then the producing conv may
     accumulate the statistics, ``conv3d(bn_sums=...)``)."""
-    sync = isinstance(bn, torch.nn.SyncBatchNorm) and torch.distributed.is_available() and \
-        torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1
-    return bool(bn.training and not sync and bn.track_running_stats and bn.momentum is not None
-                and x_dtype == torch.float16)
+    return bool(bn.training and bn.track_running_stats and bn.momentum is not None and x_dtype == torch.float16)

@@ -64,7 +64,7 @@ def main():
         runs = {
             "fwd": lambda: B.conv_gather_gemm(x, w, n_rows=n, transpose_w=False, weight_kmajor=wk, **okw),
             "dgrad": lambda: B.conv_gather_gemm(gy, w, n_rows=n, transpose_w=True, **gkw),
-            "wgrad": lambda: B.conv_wgrad(x, gy, 27, pairs, km.nbsizes32, False),
+            "wgrad": lambda: B.conv_wgrad(x, gy, 27, *km.wgrad_pairs(x), False),
         }
         omask = okw["steps"][0] if "steps" in okw else None
         if omask is not None and name[:2] not in seen_levels:

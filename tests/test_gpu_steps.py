@@ -78,3 +78,45 @@ def test_conv_epilogue_batchnorm_sums(c_in, c_out):
     yd = y.double()
     assert torch.allclose(sums[0], yd.sum(0), rtol=1e-5, atol=1e-3)
     assert torch.allclose(sums[1], (yd * yd).sum(0), rtol=1e-5, atol=1e-3)
+
+
+@pytest.mark.parametrize("use_perm", [False, True])
+def test_chunked_pair_list_and_segmented_wgrad(use_perm):
+    """b2s_kmap_pairs_chunked emits every pair exactly once in (row range, offset, row) order, and the weight
+    gradient over that segmented list equals the one over the reference-order list."""
+    import openpcseg_b200.torchsparse as ts
+    from openpcseg_b200 import backend as B
+    from openpcseg_b200.synthetic import make_batch
+    F = ts.nn.functional
+    c = torch.from_numpy(make_batch([2, 3], n_azimuth=300)["coords"]).cuda()
+    n = c.shape[0]
+    km = F.build_kernel_map(c, c, 3, (1, 1, 1))
+    k, n_chunks = km.kvol, 5
+    perm = F._tile_order(c) if use_perm else None
+    pairs, seg, total = B.kmap_pairs_chunked(km.nbr_out, perm, n_chunks)
+    m = int(total.item())
+    ref_pairs, ref_total = km.pairs()
+    assert m == int(ref_total.item()) == int(seg.sum().item())
+    got = pairs[:m].cpu().numpy()
+    nbr = km.nbr_out.cpu().numpy()
+    chunk_rows = -(-(-(-n // n_chunks)) // 32) * 32
+    rank = np.empty(n, np.int64)
+    rank[(perm.cpu().numpy() if perm is not None else np.arange(n))] = np.arange(n)
+    pos = 0
+    segs = seg.cpu().numpy().reshape(n_chunks, k)
+    for ch in range(n_chunks):
+        for kk in range(k):
+            blk = got[pos:pos + segs[ch, kk]]
+            pos += segs[ch, kk]
+            assert np.array_equal(nbr[kk][blk[:, 1]], blk[:, 0])               # a pair of offset kk
+            r = rank[blk[:, 1]]
+            assert ((r // chunk_rows) == ch).all() and (np.diff(r) > 0).all()   # in its range, launch order
+    a = sorted(map(tuple, got.tolist()))
+    b = sorted(map(tuple, ref_pairs[:m].cpu().numpy().tolist()))
+    assert a == b
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(n, 64, device="cuda", generator=g).half()
+    gy = torch.randn(n, 96, device="cuda", generator=g).half()
+    w_ref = B.conv_wgrad(x, gy, k, ref_pairs, km.nbsizes32, False)
+    w_seg = B.conv_wgrad(x, gy, k, pairs, seg, False)
+    assert float((w_ref - w_seg).abs().max()) <= 1e-4 * float(w_ref.abs().max())
