@@ -116,10 +116,13 @@ def main():
         rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
         run(f"bn_forward(+res,+relu) C={c} fp16 (stats+finalize+apply)",
             lambda: B.bn_forward(x, res, gm, bt, rm, rv, 1e-5, 0.1, True), 2 * c * n + 3 * 2 * c * n)
-        y, mean, invstd = B.bn_forward(x, res, gm, bt, rm, rv, 1e-5, 0.1, True)
+        y, mean, invstd, _ = B.bn_forward(x, res, gm, bt, rm, rv, 1e-5, 0.1, True)
         dy = torch.randn(n, c, device=dev).half()
         run(f"bn_backward(+res,+relu) C={c} fp16 (reduce+apply)",
             lambda: B.bn_backward(dy, y, x, mean, invstd, gm, True, True), 3 * 2 * c * n + 5 * 2 * c * n)
+        y2, mean2, invstd2, ss2 = B.bn_forward(x, None, gm, bt, rm, rv, 1e-5, 0.1, True)
+        run(f"bn_backward(+relu, mask from x) C={c} fp16 (reduce+apply)",
+            lambda: B.bn_backward(dy, None, x, mean2, invstd2, gm, True, False, ss2), 2 * 2 * c * n + 3 * 2 * c * n)
     f256 = torch.randn(n, 256, device=dev)
     vi = torch.randint(0, n // 4, (n,), device=dev)
     run("scatter_max C=256 fp32 (Cylinder3D)", lambda: B.scatter_max(f256, vi, n // 4), 4 * 256 * n + 8 * n + 12 * 256 * (n // 4),
