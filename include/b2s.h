@@ -286,12 +286,15 @@ int b2s_bn_forward_sums(int32_t dtype, const void* x, const void* residual, int6
  * b2s_bn_backward_apply: dx (and dres) from all-reduced sums and the global count n_total (device fp64; NULL:
  * the local n).                                                                                          */
 int b2s_bn_stats(int32_t dtype, const void* x, int64_t n, int32_t c, double* sums, b2s_stream_t stream);
+/* relu: 0 none, 1 mask from the saved output y, 2 (no residual) mask recomputed from x with the forward's
+ * scale_shift fp32 [2][c] (b2s_bn_forward's output) - y may then be NULL and is not read.             */
 int b2s_bn_backward_reduce(int32_t dtype, const void* dy, const void* y, const void* x, int64_t n, int32_t c,
-                           const float* mean, const float* invstd, int32_t relu, double* sums,
-                           b2s_stream_t stream);
+                           const float* mean, const float* invstd, int32_t relu, const float* scale_shift,
+                           double* sums, b2s_stream_t stream);
 int b2s_bn_backward_apply(int32_t dtype, const void* dy, const void* y, const void* x, int64_t n, int32_t c,
-                          const float* mean, const float* invstd, const float* gamma, int32_t relu, void* dx,
-                          void* dres, const double* sums, const double* n_total, b2s_stream_t stream);
+                          const float* mean, const float* invstd, const float* gamma, int32_t relu,
+                          const float* scale_shift, void* dx, void* dres, const double* sums,
+                          const double* n_total, b2s_stream_t stream);
 int b2s_bn_backward(int32_t dtype, const void* dy, const void* y, const void* x, int64_t n, int32_t c,
                     const float* mean, const float* invstd, const float* gamma, int32_t relu, void* dx,
                     void* dres, double* sums, b2s_stream_t stream);

@@ -69,9 +69,9 @@ _SIGNATURES = {
     "b2s_bn_forward_sums": (c_int32, [c_int32, _P, _P, c_int64, c_int32, _P, _P, c_float, c_float, _P, _P,
                                       c_int32, _P, _P, _P, _P, _P, c_int32, _P]),
     "b2s_bn_stats": (c_int32, [c_int32, _P, c_int64, c_int32, _P, _P]),
-    "b2s_bn_backward_reduce": (c_int32, [c_int32, _P, _P, _P, c_int64, c_int32, _P, _P, c_int32, _P, _P]),
+    "b2s_bn_backward_reduce": (c_int32, [c_int32, _P, _P, _P, c_int64, c_int32, _P, _P, c_int32, _P, _P, _P]),
     "b2s_bn_backward_apply": (c_int32, [c_int32, _P, _P, _P, c_int64, c_int32, _P, _P, _P, c_int32, _P, _P, _P, _P,
-                                        _P]),
+                                        _P, _P]),
     "b2s_bn_backward": (c_int32, [c_int32, _P, _P, _P, c_int64, c_int32, _P, _P, _P, c_int32, _P, _P, _P,
                                   _P]),
     "b2s_map_count": (c_int32, [_P, c_int64, c_int32, c_int32, c_int32, _P, _P]),

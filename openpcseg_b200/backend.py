@@ -532,7 +532,7 @@ def bn_forward(x: torch.Tensor, residual: Optional[torch.Tensor], gamma, beta, r
                                          stat[1].data_ptr(), stat[2].data_ptr(), sums.data_ptr(), int(ready),
                                          _stream()),
           "bn_forward", launches=2 if ready else 3)
-    return y, stat[0], stat[1]
+    return y, stat[0], stat[1], stat[2:4]
 
 
 def bn_stats(x: torch.Tensor, extra: int = 0) -> torch.Tensor:
@@ -559,22 +559,29 @@ def bn_forward_global(x, residual, gamma, beta, running_mean, running_var, eps, 
                                          _ptr(running_var), int(relu), y.data_ptr(), stat[0].data_ptr(),
                                          stat[1].data_ptr(), stat[2].data_ptr(), sums_count.data_ptr(), 2,
                                          _stream()), "bn_forward", launches=2)
-    return y, stat[0], stat[1]
+    return y, stat[0], stat[1], stat[2:4]
 
 
-def bn_backward_reduce(dy, y, x, mean, invstd, relu: bool) -> torch.Tensor:
+def _relu_mode(relu: bool, y, scale_shift) -> int:
+    """0 none / 1 mask from the saved output / 2 mask recomputed from x (no residual: y was not kept)."""
+    if not relu:
+        return 0
+    return 1 if y is not None else 2
+
+
+def bn_backward_reduce(dy, y, x, mean, invstd, relu: bool, scale_shift=None) -> torch.Tensor:
     """fp64 [2, c] = (sum dy', sum dy' * xhat) over the local rows (dy' = dy masked by the ReLU)."""
     _cuda(dy, y, x)
     dy = dy.contiguous()
     n, c = x.shape
     sums = torch.empty((2, c), dtype=torch.float64, device=x.device)
     check(_lib.lib().b2s_bn_backward_reduce(_dtype_code(x), dy.data_ptr(), _ptr(y), x.data_ptr(), n, c,
-                                            mean.data_ptr(), invstd.data_ptr(), int(relu), sums.data_ptr(),
-                                            _stream()), "bn_backward_reduce")
+                                            mean.data_ptr(), invstd.data_ptr(), _relu_mode(relu, y, scale_shift),
+                                            _ptr(scale_shift), sums.data_ptr(), _stream()), "bn_backward_reduce")
     return sums
 
 
-def bn_backward_apply(dy, y, x, mean, invstd, gamma, relu: bool, want_dres: bool, sums, n_total):
+def bn_backward_apply(dy, y, x, mean, invstd, gamma, relu: bool, want_dres: bool, sums, n_total, scale_shift=None):
     """(dx, dres | None) from (all-reduced) ``sums`` and the global row count ``n_total`` (device fp64 [1])."""
     _cuda(dy, y, x)
     dy = dy.contiguous()
@@ -582,25 +589,20 @@ def bn_backward_apply(dy, y, x, mean, invstd, gamma, relu: bool, want_dres: bool
     dx = torch.empty_like(x)
     dres = torch.empty_like(x) if want_dres else None
     check(_lib.lib().b2s_bn_backward_apply(_dtype_code(x), dy.data_ptr(), _ptr(y), x.data_ptr(), n, c,
-                                           mean.data_ptr(), invstd.data_ptr(), _ptr(gamma), int(relu),
-                                           dx.data_ptr(), _ptr(dres), sums.data_ptr(), _ptr(n_total), _stream()),
+                                           mean.data_ptr(), invstd.data_ptr(), _ptr(gamma),
+                                           _relu_mode(relu, y, scale_shift), _ptr(scale_shift), dx.data_ptr(),
+                                           _ptr(dres), sums.data_ptr(), _ptr(n_total), _stream()),
           "bn_backward_apply")
     return dx, dres
 
 
 def bn_backward(dy: torch.Tensor, y: Optional[torch.Tensor], x: torch.Tensor, mean, invstd, gamma,
-                relu: bool, want_dres: bool):
-    """Returns (dx, dres | None, d_gamma fp32 [c], d_beta fp32 [c])."""
-    _cuda(dy, y, x)
-    dy = dy.contiguous()
-    n, c = x.shape
-    dx = torch.empty_like(x)
-    dres = torch.empty_like(x) if want_dres else None
-    sums = torch.empty((2, c), dtype=torch.float64, device=x.device)
-    check(_lib.lib().b2s_bn_backward(_dtype_code(x), dy.data_ptr(), _ptr(y), x.data_ptr(), n, c,
-                                     mean.data_ptr(), invstd.data_ptr(), _ptr(gamma), int(relu),
-                                     dx.data_ptr(), _ptr(dres), sums.data_ptr(), _stream()),
-          "bn_backward", launches=2)
+                relu: bool, want_dres: bool, scale_shift=None):
+    """Returns (dx, dres | None, d_gamma fp32 [c], d_beta fp32 [c]).  ``y`` None with ``relu``: the mask is
+    recomputed from x and ``scale_shift`` (no-residual layers do not keep their output for backward)."""
+    sums = bn_backward_reduce(dy, y, x, mean, invstd, relu, scale_shift)
+    dx, dres = bn_backward_apply(dy, y, x, mean, invstd, gamma, relu, want_dres, sums, None, scale_shift)
+    STATS["launches"] += 0
     return dx, dres, sums[1].float(), sums[0].float()
 
 

@@ -162,12 +162,22 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const T* __restric
   }
 }
 
+// ReLU mask of the forward pass: relu == 1 reads the saved output (y > 0); relu == 2 (no residual) recomputes
+// it from x with the forward's own scale / shift and expression, so the backward pass reads one tensor less
+// in each of its two kernels and the autograd graph does not keep y alive for it.
+template <typename T>
+__device__ __forceinline__ bool relu_open_from_x(float x, float a, float b) {
+  const float f = fmaxf(fmaf(x, a, b), 0.f);
+  if constexpr (sizeof(T) == 2) return __half2float(__float2half_rn(f)) > 0.f;
+  else return f > 0.f;
+}
+
 // g = dy * (y > 0 if relu);  sums[0][c] += sum g;  sums[1][c] += sum g * xhat
 template <typename T>
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
     const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ x, int64_t n, int c,
     const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
-    double* __restrict__ sums) {
+    const float* __restrict__ scale_shift, double* __restrict__ sums) {
   constexpr int W = VecT<T>::W;
   extern __shared__ float s_part[];
   for (int t = threadIdx.x; t < 2 * c; t += blockDim.x) s_part[t] = 0.f;
@@ -177,11 +187,13 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
   const int rows_per_block = blockDim.x / groups;
   const int rl = threadIdx.x / groups;
   if (rl < rows_per_block) {
-    float m[W], is[W], sg[W], sgx[W];
+    float m[W], is[W], sg[W], sgx[W], sa[W], sb[W];
 #pragma unroll
     for (int j = 0; j < W; ++j) {
       m[j] = __ldg(mean + cg * W + j);
       is[j] = __ldg(invstd + cg * W + j);
+      sa[j] = relu == 2 ? __ldg(scale_shift + cg * W + j) : 0.f;
+      sb[j] = relu == 2 ? __ldg(scale_shift + c + cg * W + j) : 0.f;
       sg[j] = sgx[j] = 0.f;
     }
     for (int64_t r = (int64_t)blockIdx.x * rows_per_block + rl; r < n;
@@ -190,11 +202,12 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
       VecT<T> vd, vx, vy;
       vd.load(dy + off);
       vx.load(x + off);
-      if (relu) vy.load(y + off);
+      if (relu == 1) vy.load(y + off);
 #pragma unroll
       for (int j = 0; j < W; ++j) {
         float g = vd.get(j);
-        if (relu && !(vy.get(j) > 0.f)) g = 0.f;
+        if (relu == 1 && !(vy.get(j) > 0.f)) g = 0.f;
+        if (relu == 2 && !relu_open_from_x<T>(vx.get(j), sa[j], sb[j])) g = 0.f;
         sg[j] += g;
         sgx[j] = fmaf(g, (vx.get(j) - m[j]) * is[j], sgx[j]);
       }
@@ -214,15 +227,15 @@ template <typename T>
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
     const T* __restrict__ dy, const T* __restrict__ y, const T* __restrict__ x, int64_t n, int c,
     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-    const double* __restrict__ sums, const double* __restrict__ n_dev, int relu, T* __restrict__ dx,
-    T* __restrict__ dres) {
+    const double* __restrict__ sums, const double* __restrict__ n_dev, int relu,
+    const float* __restrict__ scale_shift, T* __restrict__ dx, T* __restrict__ dres) {
   constexpr int W = VecT<T>::W;
   const int groups = c / W;
   const int cg = threadIdx.x % groups;
   const int rows_per_block = blockDim.x / groups;
   const int rl = threadIdx.x / groups;
   if (rl >= rows_per_block) return;
-  float m[W], is[W], k0[W], k1[W], k2[W];
+  float m[W], is[W], k0[W], k1[W], k2[W], sa[W], sb[W];
   const float inv_n = n_dev ? (float)(1.0 / *n_dev) : 1.f / (float)n;   // sums are global under sync BN
 #pragma unroll
   for (int j = 0; j < W; ++j) {
@@ -230,6 +243,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
     m[j] = __ldg(mean + ch);
     is[j] = __ldg(invstd + ch);
     const float gi = (gamma ? __ldg(gamma + ch) : 1.f) * is[j];
+    sa[j] = relu == 2 ? __ldg(scale_shift + ch) : 0.f;
+    sb[j] = relu == 2 ? __ldg(scale_shift + c + ch) : 0.f;
     k0[j] = gi;                                         // * g
     k1[j] = gi * (float)(sums[ch] * (double)inv_n);     // mean of g
     k2[j] = gi * (float)(sums[c + ch] * (double)inv_n); // mean of g * xhat
@@ -240,11 +255,12 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
     VecT<T> vd, vx, vy, o, og;
     vd.load(dy + off);
     vx.load(x + off);
-    if (relu) vy.load(y + off);
+    if (relu == 1) vy.load(y + off);
 #pragma unroll
     for (int j = 0; j < W; ++j) {
       float g = vd.get(j);
-      if (relu && !(vy.get(j) > 0.f)) g = 0.f;
+      if (relu == 1 && !(vy.get(j) > 0.f)) g = 0.f;
+      if (relu == 2 && !relu_open_from_x<T>(vx.get(j), sa[j], sb[j])) g = 0.f;
       const float xhat = (vx.get(j) - m[j]) * is[j];
       o.set(j, k0[j] * g - k1[j] - k2[j] * xhat);
       og.set(j, g);
@@ -339,10 +355,11 @@ int b2s_bn_stats(int32_t dtype, const void* x, int64_t n, int32_t c, double* sum
 }
 
 int b2s_bn_backward_reduce(int32_t dtype, const void* dy, const void* y, const void* x, int64_t n, int32_t c,
-                           const float* mean, const float* invstd, int32_t relu, double* sums,
-                           b2s_stream_t stream) {
+                           const float* mean, const float* invstd, int32_t relu, const float* scale_shift,
+                           double* sums, b2s_stream_t stream) {
   B2S_REQUIRE(dtype == B2S_F32 || dtype == B2S_F16, B2S_ERR_INVALID, "b2s_bn_backward: dtype");
-  B2S_REQUIRE(n >= 1 && c >= 1 && dy && x && mean && invstd && sums && (!relu || y), B2S_ERR_INVALID,
+  B2S_REQUIRE(n >= 1 && c >= 1 && dy && x && mean && invstd && sums && (relu != 1 || y) &&
+                  (relu != 2 || scale_shift) && relu >= 0 && relu <= 2, B2S_ERR_INVALID,
               "b2s_bn_backward: bad argument");
   B2S_REQUIRE(bn_shape_ok(dtype, c), B2S_ERR_UNSUPPORTED, "b2s_bn_backward: C=%d not a vector multiple", c);
   cudaStream_t st = as_stream(stream);
@@ -352,20 +369,22 @@ int b2s_bn_backward_reduce(int32_t dtype, const void* dy, const void* y, const v
   if (dtype == B2S_F16)
     bn_bwd_reduce_kernel<__half><<<grid, kBnThreads, sh, st>>>(
         reinterpret_cast<const __half*>(dy), reinterpret_cast<const __half*>(y),
-        reinterpret_cast<const __half*>(x), n, c, mean, invstd, relu, sums);
+        reinterpret_cast<const __half*>(x), n, c, mean, invstd, relu, scale_shift, sums);
   else
     bn_bwd_reduce_kernel<float><<<grid, kBnThreads, sh, st>>>(
         reinterpret_cast<const float*>(dy), reinterpret_cast<const float*>(y),
-        reinterpret_cast<const float*>(x), n, c, mean, invstd, relu, sums);
+        reinterpret_cast<const float*>(x), n, c, mean, invstd, relu, scale_shift, sums);
   B2S_CHECK_LAUNCH("b2s_bn_backward_reduce");
   return B2S_OK;
 }
 
 int b2s_bn_backward_apply(int32_t dtype, const void* dy, const void* y, const void* x, int64_t n, int32_t c,
-                          const float* mean, const float* invstd, const float* gamma, int32_t relu, void* dx,
-                          void* dres, const double* sums, const double* n_total, b2s_stream_t stream) {
+                          const float* mean, const float* invstd, const float* gamma, int32_t relu,
+                          const float* scale_shift, void* dx, void* dres, const double* sums,
+                          const double* n_total, b2s_stream_t stream) {
   B2S_REQUIRE(dtype == B2S_F32 || dtype == B2S_F16, B2S_ERR_INVALID, "b2s_bn_backward: dtype");
-  B2S_REQUIRE(n >= 1 && c >= 1 && dy && x && dx && mean && invstd && sums && (!relu || y), B2S_ERR_INVALID,
+  B2S_REQUIRE(n >= 1 && c >= 1 && dy && x && dx && mean && invstd && sums && (relu != 1 || y) &&
+                  (relu != 2 || scale_shift) && relu >= 0 && relu <= 2, B2S_ERR_INVALID,
               "b2s_bn_backward: bad argument");
   B2S_REQUIRE(bn_shape_ok(dtype, c), B2S_ERR_UNSUPPORTED, "b2s_bn_backward: C=%d not a vector multiple", c);
   cudaStream_t st = as_stream(stream);
@@ -373,12 +392,12 @@ int b2s_bn_backward_apply(int32_t dtype, const void* dy, const void* y, const vo
   if (dtype == B2S_F16)
     bn_bwd_apply_kernel<__half><<<grid, kBnThreads, 0, st>>>(
         reinterpret_cast<const __half*>(dy), reinterpret_cast<const __half*>(y),
-        reinterpret_cast<const __half*>(x), n, c, mean, invstd, gamma, sums, n_total, relu,
+        reinterpret_cast<const __half*>(x), n, c, mean, invstd, gamma, sums, n_total, relu, scale_shift,
         reinterpret_cast<__half*>(dx), reinterpret_cast<__half*>(dres));
   else
     bn_bwd_apply_kernel<float><<<grid, kBnThreads, 0, st>>>(
         reinterpret_cast<const float*>(dy), reinterpret_cast<const float*>(y),
-        reinterpret_cast<const float*>(x), n, c, mean, invstd, gamma, sums, n_total, relu,
+        reinterpret_cast<const float*>(x), n, c, mean, invstd, gamma, sums, n_total, relu, scale_shift,
         reinterpret_cast<float*>(dx), reinterpret_cast<float*>(dres));
   B2S_CHECK_LAUNCH("b2s_bn_backward_apply");
   return B2S_OK;
@@ -388,9 +407,10 @@ int b2s_bn_backward(int32_t dtype, const void* dy, const void* y, const void* x,
                     const float* mean, const float* invstd, const float* gamma, int32_t relu, void* dx,
                     void* dres, double* sums /*[2][c]: d_beta, d_gamma on return*/,
                     b2s_stream_t stream) {
-  int rc = b2s_bn_backward_reduce(dtype, dy, y, x, n, c, mean, invstd, relu, sums, stream);
+  int rc = b2s_bn_backward_reduce(dtype, dy, y, x, n, c, mean, invstd, relu ? 1 : 0, nullptr, sums, stream);
   if (rc != B2S_OK) return rc;
-  return b2s_bn_backward_apply(dtype, dy, y, x, n, c, mean, invstd, gamma, relu, dx, dres, sums, nullptr, stream);
+  return b2s_bn_backward_apply(dtype, dy, y, x, n, c, mean, invstd, gamma, relu ? 1 : 0, nullptr, dx, dres, sums,
+                               nullptr, stream);
 }
 
 }  // extern "C"

@@ -46,8 +46,8 @@ __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 // wait of a role that is a whole tile away from its event: poll, then sleep with doubling back-off
-__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
-  uint32_t ns = 64;
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t cap_ns) {
+  uint32_t ns = 32;
   while (true) {
     uint32_t done;
     asm volatile(
@@ -60,8 +60,10 @@ __device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity), "r"(kWaitHintNs)
         : "memory");
     if (done) break;
-    __nanosleep(ns);
-    if (ns < 2048) ns <<= 1;
+    if (cap_ns) {
+      __nanosleep(ns);
+      if (ns < cap_ns) ns <<= 1;
+    }
   }
 }
 
@@ -109,8 +111,9 @@ struct Params {
   int n64, tail32, merge_tail; // c_red = 64 n64 + 32 tail32; merge: tail shares the last wide stage
   int stages, stage_stride;
   int acc_stride, acc_bufs, tmem_cols;
-  int dbg;                     // ablation (B2S_TC4_DBG): 1 no gathers, 2 no weight TMA, 4 no MMAs, 8 no stores
+  int dbg;                     // ablation (B2S_TC4_DBG): 1 no gathers, 2 no weight TMA, 4 no MMAs, 8 no stores, 16 no epilogue body
   int wait_ns;                 // suspend-time hint of the pipeline waits (B2S_TC4_WAIT_NS; 0 = spin)
+  int sleep_ns;                // cap of the epilogue's back-off sleep (B2S_TC4_SLEEP_NS; 0 = no sleep)
 };
 
 struct Ring {
@@ -394,16 +397,20 @@ __global__ void __launch_bounds__(128 * T + 192) gather_gemm_tc4_kernel(
       const int64_t ro0 = (p.row_perm && r_t0 < p.n_rows) ? (int64_t)__ldg(p.row_perm + r_t0) : r_t0;
       const int64_t ro1 = (T == 2 && p.row_perm && r_t1 < p.n_rows) ? (int64_t)__ldg(p.row_perm + r_t1) : r_t1;
       if (any) {
-        mbar_wait_sleep(smem_u32(&s_acc_full[ab]), turn & 1);     // a whole main loop away: sleep
+        mbar_wait_sleep(smem_u32(&s_acc_full[ab]), turn & 1, (uint32_t)p.sleep_ns);   // a whole main loop away
         tc_fence_after();
       }
 #pragma unroll 1
-      for (int t = 0; t < T; ++t) {
+      for (int t = 0; t < T && !(p.dbg & 16); ++t) {
         const int64_t r = t == 0 ? r_t0 : r_t1;
         const int64_t r_out = t == 0 ? ro0 : ro1;
         const bool live = r < p.n_rows;
         const uint32_t t_lane = tmem_base + (uint32_t)((ab * T + t) * p.acc_stride) + ((uint32_t)(q * 32) << 16);
-        for (int c0 = 0; c0 < p.c_res; c0 += 16) {
+        // 16 columns per TMEM load (the 32-column form was measured: more registers, spills, +6 % kernel time);
+        // fp32 -> fp16 two at a time; the epilogue warps share issue slots with the gather warps (ablation: no
+        // epilogue body = -19 % kernel time), so every instruction here counts
+        for (int c0 = 0; c0 < p.c_res;) {
+          constexpr int w = 16;
           uint32_t v[16];
           if (any) {
             tmem_ld16(t_lane + (uint32_t)c0, v);
@@ -412,49 +419,61 @@ __global__ void __launch_bounds__(128 * T + 192) gather_gemm_tc4_kernel(
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = 0u;
           }
-          __align__(16) __half h[16];
+          uint32_t hp[8];                                    // packed half2
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float f = __uint_as_float(v[j]);
-            if (p.bias) f += __half2float(__ldg(p.bias + c0 + j));
-            h[j] = __float2half_rn(f);
+          for (int j = 0; j < 8; ++j) {
+            float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
+            if (p.bias && 2 * j < w) {
+              f0 += __half2float(__ldg(p.bias + c0 + 2 * j));
+              f1 += __half2float(__ldg(p.bias + c0 + 2 * j + 1));
+            }
+            const __half2 h2 = __floats2half2_rn(f0, f1);
+            hp[j] = *reinterpret_cast<const uint32_t*>(&h2);
           }
           if (live && !(p.dbg & 8)) {
             uint4* dst = reinterpret_cast<uint4*>(p.out + r_out * p.c_res + c0);
-            dst[0] = reinterpret_cast<const uint4*>(h)[0];
-            dst[1] = reinterpret_cast<const uint4*>(h)[1];
+            dst[0] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            dst[1] = make_uint4(hp[4], hp[5], hp[6], hp[7]);
           }
           if (p.bn_sums) {
             // per-column sum / sum of squares of the fp16 values just written, over the warp's 32 rows:
             // halving exchange (16 + 8 + 4 + 2 + 1 column slots survive per lane), then one shared-memory
             // atomic per column from the lanes that end up owning it
-            float a[16], b[16];
+            {
+              constexpr int h0 = 0;
+              float a[16], b[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float f = live ? __half2float(h[j]) : 0.f;
-              a[j] = f;
-              b[j] = f * f;
-            }
+              for (int j = 0; j < 8; ++j) {
+                const uint32_t u = hp[j];
+                const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&u));
+                const float x0 = live ? f2.x : 0.f, x1 = live ? f2.y : 0.f;
+                a[2 * j] = x0;
+                a[2 * j + 1] = x1;
+                b[2 * j] = x0 * x0;
+                b[2 * j + 1] = x1 * x1;
+              }
 #pragma unroll
-            for (int width = 8, bit = 16; width >= 1; width >>= 1, bit >>= 1) {
-              const bool upper = (lane & bit) != 0;
+              for (int width = 8, bit = 16; width >= 1; width >>= 1, bit >>= 1) {
+                const bool upper = (lane & bit) != 0;
 #pragma unroll
-              for (int j = 0; j < width; ++j) {
-                const float sa = upper ? a[j] : a[j + width], sb = upper ? b[j] : b[j + width];
-                const float ka = upper ? a[j + width] : a[j], kb = upper ? b[j + width] : b[j];
-                a[j] = ka + __shfl_xor_sync(0xffffffffu, sa, bit);
-                b[j] = kb + __shfl_xor_sync(0xffffffffu, sb, bit);
+                for (int j = 0; j < width; ++j) {
+                  const float sa = upper ? a[j] : a[j + width], sb = upper ? b[j] : b[j + width];
+                  const float ka = upper ? a[j + width] : a[j], kb = upper ? b[j + width] : b[j];
+                  a[j] = ka + __shfl_xor_sync(0xffffffffu, sa, bit);
+                  b[j] = kb + __shfl_xor_sync(0xffffffffu, sb, bit);
+                }
+              }
+              a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+              b[0] += __shfl_xor_sync(0xffffffffu, b[0], 1);
+              if ((lane & 1) == 0) {
+                const int col = c0 + h0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
+                                ((lane >> 1) & 1);
+                atomicAdd(&s_stat[col], a[0]);
+                atomicAdd(&s_stat[p.c_res + col], b[0]);
               }
             }
-            a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
-            b[0] += __shfl_xor_sync(0xffffffffu, b[0], 1);
-            if ((lane & 1) == 0) {
-              const int col = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 +
-                              ((lane >> 1) & 1);
-              atomicAdd(&s_stat[col], a[0]);
-              atomicAdd(&s_stat[p.c_res + col], b[0]);
-            }
           }
+          c0 += w;
         }
       }
       if (any) {
@@ -551,9 +570,10 @@ bool tc_make_row_map(CUtensorMap* tm, const void* base, int64_t rows, int cols, 
 int tc4_tile_rows(int c_res, int64_t n_rows) {
   int stride = 32;
   while (stride < c_res) stride <<= 1;
-  // T = 2 (256-row CTA tiles sharing each weight tile) pays only where a step is a single 32-channel
-  // stage (profiles/r1_conv_microbench_v3.txt: 175 -> 122 us at C_res = 32)
-  int T = stride <= 32 ? 2 : 1;
+  // T = 2 (256-row CTA tiles sharing each weight tile) was a win for C_res <= 32 in revision 3 (175 -> 122 us);
+  // with step tables the 128-row form wins everywhere (batch 16, 32 -> 32: 289 -> 216 us, profiles/r2_tile_order.txt)
+  // - kept behind B2S_TC_T=2 for experiments
+  int T = 1;
   {
     const char* et = getenv("B2S_TC_T");
     if (et && (atoi(et) == 1 || atoi(et) == 2) && stride * atoi(et) <= 512) T = atoi(et);
@@ -634,6 +654,8 @@ int launch_gather_gemm_tc4(const void* in, int64_t n_src, const void* wt, int k,
     if (ed) p.dbg = atoi(ed);
     const char* ew = getenv("B2S_TC4_WAIT_NS");
     if (ew) p.wait_ns = atoi(ew);
+    const char* es = getenv("B2S_TC4_SLEEP_NS");
+    p.sleep_ns = es ? atoi(es) : 256;
   }
   {
     const char* es = getenv("B2S_TC_STAGES");

@@ -185,7 +185,10 @@ class KernelMap:
             # rows with the same neighbourhood pattern share tiles (rarest offsets first), see
             # b2s_tile_order_key: 25 % of the (tile, offset) steps stay active at stride 1 vs 61 % for (z,x,y)
             keys, self._row_bits = B.tile_order_key(self.nbr_out, self.nbsizes32, self._coords, self._shift)
-            self.tile_perm = torch.argsort(keys).int()
+            perm = torch.argsort(keys).int()
+            if _TILE_SPATIAL:
+                perm = _spatial_tile_order(perm, self._coords, self._shift)
+            self.tile_perm = perm
         else:
             self.tile_perm = _tile_order(self._coords)
 
@@ -233,6 +236,30 @@ _TILE_ORDER = os.environ.get("B2S_TILE_ORDER", "mask")      # "mask" | "zxy" | "
 # turns both operands into scattered gathers and doubles the number of small work units
 _WGRAD_CHUNKED = os.environ.get("B2S_WGRAD_CHUNKED", "0") == "1"
 _WGRAD_CHUNK_ROWS = int(os.environ.get("B2S_WGRAD_CHUNK_ROWS", 65536))
+_TILE_SPATIAL = os.environ.get("B2S_TILE_SPATIAL", "0") == "1"
+_TILE_SPATIAL_BITS = int(os.environ.get("B2S_TILE_SPATIAL_BITS", 5))      # block = 2^bits cells of the level
+
+
+def _spatial_tile_order(perm: torch.Tensor, coords: torch.Tensor, shift: int) -> torch.Tensor:
+    """Keep the COMPOSITION of the 128-row tiles (rows grouped by neighbourhood pattern: best fill) but walk the
+    tiles in the order of a coarse (x, y) block of their first row instead of pattern by pattern.  The persistent
+    CTAs take consecutive tiles, so the ~300 tiles in flight then cover one neighbourhood of the scene and the
+    rows they gather (each needed by ~4.7 offsets / tiles) are re-used from L2; in pattern order the tiles in
+    flight are scattered over the whole batch and a 16-scan level (290 MB of rows at 96 channels) streams from
+    HBM once per gather."""
+    n = perm.shape[0]
+    g = 256                        # granule = the largest CTA tile, so 256-row tiles keep their composition too
+    t = n // g
+    if t < 2:
+        return perm
+    first = perm[: t * g: g].long()
+    c = coords.index_select(0, first).long()
+    blk = shift + _TILE_SPATIAL_BITS
+    key = (((c[:, 0] >> blk) & 0xFFF) << 44) | (((c[:, 1] >> blk) & 0xFFF) << 32) | \
+        torch.arange(t, device=perm.device, dtype=torch.int64)
+    order = torch.argsort(key)
+    body = perm[: t * g].view(t, g).index_select(0, order).reshape(-1)
+    return torch.cat([body, perm[t * g:]])
 
 
 def _tile_order(coords: torch.Tensor) -> torch.Tensor:
@@ -482,19 +509,22 @@ class _BatchNormAct(Function):
 
     @staticmethod
     def forward(ctx, x, residual, gamma, beta, running_mean, running_var, eps, momentum, relu, sums=None):
-        y, mean, invstd = B.bn_forward(x, residual, gamma, beta, running_mean, running_var, eps, momentum,
-                                       relu, sums)
-        ctx.save_for_backward(x, y if relu else None, mean, invstd, gamma)
-        ctx.relu, ctx.has_res = relu, residual is not None
-        ctx.mark_non_differentiable(mean, invstd)
+        y, mean, invstd, scale_shift = B.bn_forward(x, residual, gamma, beta, running_mean, running_var, eps,
+                                                    momentum, relu, sums)
+        has_res = residual is not None
+        # ReLU mask of the backward pass: from y when a residual was added, else recomputed from x (saves a
+        # read of y in both backward kernels and does not keep y alive for autograd)
+        ctx.save_for_backward(x, y if (relu and has_res) else None, mean, invstd, gamma,
+                              scale_shift if (relu and not has_res) else None)
+        ctx.relu, ctx.has_res = relu, has_res
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        x, y, mean, invstd, gamma = ctx.saved_tensors
+        x, y, mean, invstd, gamma, scale_shift = ctx.saved_tensors
         dx, dres, dgamma, dbeta = B.bn_backward(dy, y, x, mean, invstd, gamma, ctx.relu,
-                                                ctx.has_res and ctx.needs_input_grad[1])
+                                                ctx.has_res and ctx.needs_input_grad[1], scale_shift)
         return (dx, dres, dgamma.to(gamma.dtype) if gamma is not None else None,
                 dbeta.to(gamma.dtype) if gamma is not None else None, None, None, None, None, None, None)
 
@@ -513,22 +543,24 @@ class _SyncBatchNormAct(Function):
         buf = B.bn_stats(x, extra=1) if sums is None else torch.cat([sums.reshape(-1), sums.new_zeros(1)])
         buf[2 * c] = float(x.shape[0])
         dist.all_reduce(buf, group=group)
-        y, mean, invstd = B.bn_forward_global(x, residual, gamma, beta, running_mean, running_var, eps, momentum,
-                                              relu, buf)
-        ctx.save_for_backward(x, y if relu else None, mean, invstd, gamma, buf[2 * c:])
-        ctx.relu, ctx.has_res, ctx.group = relu, residual is not None, group
+        y, mean, invstd, scale_shift = B.bn_forward_global(x, residual, gamma, beta, running_mean, running_var,
+                                                           eps, momentum, relu, buf)
+        has_res = residual is not None
+        ctx.save_for_backward(x, y if (relu and has_res) else None, mean, invstd, gamma, buf[2 * c:],
+                              scale_shift if (relu and not has_res) else None)
+        ctx.relu, ctx.has_res, ctx.group = relu, has_res, group
         return y
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
         import torch.distributed as dist
-        x, y, mean, invstd, gamma, n_total = ctx.saved_tensors
-        local = B.bn_backward_reduce(dy, y, x, mean, invstd, ctx.relu)
+        x, y, mean, invstd, gamma, n_total, scale_shift = ctx.saved_tensors
+        local = B.bn_backward_reduce(dy, y, x, mean, invstd, ctx.relu, scale_shift)
         glob = local.clone()
         dist.all_reduce(glob, group=ctx.group)
         dx, dres = B.bn_backward_apply(dy, y, x, mean, invstd, gamma, ctx.relu,
-                                       ctx.has_res and ctx.needs_input_grad[1], glob, n_total)
+                                       ctx.has_res and ctx.needs_input_grad[1], glob, n_total, scale_shift)
         dgamma = local[1].float().to(gamma.dtype) if gamma is not None else None
         dbeta = local[0].float().to(gamma.dtype) if gamma is not None else None
         return (dx, dres, dgamma, dbeta) + (None,) * 7

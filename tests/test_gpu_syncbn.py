@@ -44,8 +44,9 @@ def _worker(rank, world, port, c, out):
         rs = res[sl].cuda().requires_grad_(True)
         y = batch_norm_act(xs, bn, relu=True, residual=rs)
         y.backward(dy[sl].cuda())
-        out.put((rank, y.detach().float().cpu(), xs.grad.float().cpu(), rs.grad.float().cpu(),
-                 bn.weight.grad.cpu(), bn.bias.grad.cpu(), bn.running_mean.cpu(), bn.running_var.cpu()))
+        # numpy payloads are pickled by value (torch tensors travel as shared-memory handles that die with the worker)
+        out.put((rank,) + tuple(t.detach().float().cpu().numpy() for t in
+                                (y, xs.grad, rs.grad, bn.weight.grad, bn.bias.grad, bn.running_mean, bn.running_var)))
     finally:
         dist.destroy_process_group()
 
@@ -60,6 +61,7 @@ def test_sync_batchnorm_two_ranks_equals_full_batch(c):
     for p in procs:
         p.start()
     got = sorted([out.get(timeout=180) for _ in range(2)], key=lambda t: t[0])
+    got = [(g[0],) + tuple(torch.from_numpy(a) for a in g[1:]) for g in got]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
