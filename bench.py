@@ -84,6 +84,10 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-config1", action="store_true")
+    ap.add_argument("--bucket-mb", type=int, default=1024,
+                    help="DDP bucket_cap_mb.  Default: ONE bucket = the gradient all-reduce runs after backward "
+                         "instead of under it: NCCL's CTAs otherwise take SM slots from the persistent conv grids, "
+                         "whose statically striped CTAs then finish in a second wave (N = 8: 0.89 -> see profiles/)")
     ap.add_argument("--same-data", action="store_true",
                     help="diagnostic: every rank gets rank 0's scans (separates load imbalance from communication)")
     ap.add_argument("--cpu-budget-s", type=float, default=None,
@@ -389,7 +393,8 @@ def main():
     model.train()
     net = model
     if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
+                                                        bucket_cap_mb=args.bucket_mb)
     # SGD momentum 0.9, weight decay 1e-4 (pcseg/optim/__init__.py:15-21 - the reference never passes
     # NESTEROV on), AMP GradScaler, clip 10 (train.py:367-372); lr is irrelevant to throughput
     opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
@@ -532,7 +537,7 @@ def main():
             "config": {"workload": workload, "name": args.config, "model_src": args.model_src,
                        "scans_per_gpu_per_step": args.batch, "voxels_per_scan": int(vox_per_scan),
                        "amp": amp, "sync_bn": bool(args.sync_bn and world > 1),
-                       "parallelism": f"dp{world}", "sm_reserve": reserve,
+                       "parallelism": f"dp{world}", "sm_reserve": reserve, "ddp_bucket_mb": args.bucket_mb,
                        "l2": "256 MiB flush write before every step",
                        "peaks": pk},
             "clocks": clocks,

@@ -429,9 +429,29 @@ def _pad_for_tensor_cores(feats: torch.Tensor, weight: torch.Tensor):
     return feats, weight, (c_out if pad_out else None)
 
 
-def _can_fuse_sums(bn_sums, feats, weight, keep_out, bias) -> bool:
-    return (bn_sums is not None and keep_out is None and bias is None and weight.ndim == 3
-            and weight.shape[2] <= 512 and B.conv_steps_supported(feats, weight.shape[1], weight.shape[2]))
+_AUTO_BN_SUMS = os.environ.get("B2S_AUTO_BN_SUMS", "1") != "0"
+
+
+def _auto_sums(bn_sums, feats, weight, keep_out, bias):
+    """The fp64 [2, C_out] statistics buffer the conv epilogue should fill, or None.  A caller may pass one
+    (``conv3d(bn_sums=...)``); otherwise every bias-free training-time conv on the step-table kernel gets one
+    speculatively - the reference's blocks are conv -> BatchNorm (minkunet.py:66-72, 100-114) and the batch norm
+    that follows then skips its own pass over [N, C]; a conv without a norm behind it wastes one memset."""
+    ok = (keep_out is None and bias is None and weight.ndim == 3 and weight.shape[2] <= 512
+          and B.conv_steps_supported(feats, weight.shape[1], weight.shape[2]))
+    if not ok:
+        return None
+    if bn_sums is None and _AUTO_BN_SUMS and torch.is_grad_enabled() and weight.requires_grad:
+        bn_sums = torch.zeros((2, weight.shape[2]), dtype=torch.float64, device=feats.device)
+    return bn_sums
+
+
+def _fused_sums(x: torch.Tensor):
+    """Statistics attached to ``x`` by the conv that produced it, if ``x`` was not modified since."""
+    tag = getattr(x, "_b2s_sums", None)
+    if tag is None or tag[1] != x._version or tag[0].shape[1] != x.shape[1]:
+        return None
+    return tag[0]
 
 
 def conv3d(input: SparseTensor, weight: torch.Tensor,
@@ -466,18 +486,18 @@ def conv3d(input: SparseTensor, weight: torch.Tensor,
         if key not in input.kmaps:
             input.kmaps[key] = build_kernel_map(input.coords, out_coords, kernel_size, input.stride,
                                                 dilation)
-        fuse = _can_fuse_sums(bn_sums, feats, weight, keep_out, bias)
-        out_feats = ConvolutionFunction.apply(feats, weight, input.kmaps[key], False, bn_sums if fuse else None)
-        if fuse:
-            out_feats._b2s_sums = bn_sums
+        bn_sums = _auto_sums(bn_sums, feats, weight, keep_out, bias)
+        out_feats = ConvolutionFunction.apply(feats, weight, input.kmaps[key], False, bn_sums)
+        if bn_sums is not None:
+            out_feats._b2s_sums = (bn_sums, out_feats._version)
     else:
         out_stride = tuple(input.stride[a] // stride[a] for a in range(3))
         out_coords = input.cmaps[out_stride]
         kmap = input.kmaps[(out_stride, kernel_size, stride, dilation)]
-        fuse = _can_fuse_sums(bn_sums, feats, weight, keep_out, bias)
-        out_feats = ConvolutionFunction.apply(feats, weight, kmap, True, bn_sums if fuse else None)
-        if fuse:
-            out_feats._b2s_sums = bn_sums
+        bn_sums = _auto_sums(bn_sums, feats, weight, keep_out, bias)
+        out_feats = ConvolutionFunction.apply(feats, weight, kmap, True, bn_sums)
+        if bn_sums is not None:
+            out_feats._b2s_sums = (bn_sums, out_feats._version)
 
     if keep_out is not None:
         # contiguous: a strided [N, C] view sends torch's batch norm to its generic (non channels-last)
@@ -579,7 +599,7 @@ def batch_norm_act(x: torch.Tensor, bn: torch.nn.modules.batchnorm._BatchNorm, r
         with torch.no_grad():
             bn.num_batches_tracked += 1
         return _SyncBatchNormAct.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
-                                       bn.momentum, relu, bn.process_group, getattr(x, "_b2s_sums", None))
+                                       bn.momentum, relu, bn.process_group, _fused_sums(x))
     if not usable:
         # the dense implementation of the module's class on the [N, C] rows (the sparse wrappers'
         # own forward expects a SparseTensor)
@@ -591,7 +611,7 @@ def batch_norm_act(x: torch.Tensor, bn: torch.nn.modules.batchnorm._BatchNorm, r
     with torch.no_grad():
         bn.num_batches_tracked += 1
     return _BatchNormAct.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
-                               bn.momentum, relu, getattr(x, "_b2s_sums", None))
+                               bn.momentum, relu, _fused_sums(x))
 
 
 def batch_norm_fusable(x_dtype: torch.dtype, bn: torch.nn.modules.batchnorm._BatchNorm) -> bool:
