@@ -454,10 +454,23 @@ int launch_wgrad_tc(const void* in, int64_t n_in, const void* gout, int64_t n_ou
   }
   p.tmem_cols = tc::tmem_cols_for(c_out);
   const int stage = (2 + (c_out + 63) / 64) * kPanelBytes;
-  // 228 KiB per SM, 1 KiB reserved per CTA, ~8.5 KiB static (segment prefixes + barriers), 1 KiB alignment slack
-  int stages = (int)((103 * 1024) / stage);          // two CTAs per SM when >= 3 stages fit twice
-  const bool two_per_sm = stages >= 3 && p.tmem_cols <= 256;
-  if (!two_per_sm) stages = (int)((214 * 1024) / stage);
+  // CTAs per SM: as many as fit with a 2-stage ring each (every CTA is one independent gather -> MMA -> commit
+  // chain, and the chains, not the ring depth, are what hide the hand-shake and gather latencies: 256-channel
+  // layers went 150 -> 109 us from 1 x 4 stages to 2 x 2 stages, profiles/r2_wgrad_ctas.txt).  Budget: 228 KiB
+  // per SM, per CTA 1 KiB reserved + ~8.5 KiB static (segment prefixes, barriers) + 1 KiB alignment slack.
+  static const int max_ctas = [] {
+    const char* e = getenv("B2S_WG_CTAS");
+    return e ? atoi(e) : 3;
+  }();
+  int ctas = 1, stages = 0;
+  for (int c = max_ctas < 1 ? 1 : (max_ctas > 4 ? 4 : max_ctas); c >= 1; --c) {
+    const int st = (int)(((228 * 1024) / c - 11 * 1024) / stage);
+    if ((st >= 2 && c * p.tmem_cols <= 512) || c == 1) {
+      ctas = c;
+      stages = st;
+      break;
+    }
+  }
   if (stages > 6) stages = 6;
   B2S_REQUIRE(stages >= 2, B2S_ERR_UNSUPPORTED, "b2s_conv_wgrad: tile does not fit (C_out=%d)", c_out);
   p.stages = stages;
@@ -467,7 +480,7 @@ int launch_wgrad_tc(const void* in, int64_t n_in, const void* gout, int64_t n_ou
   // (the true pair count lives on the device; on LiDAR surfaces ~1/4 of the K*N slots exist)
   const int sms = persistent_sms();
   const int64_t est = k > 1 ? n_pairs_bound / 4 + 1 : n_pairs_bound;
-  const int64_t slots_est = (int64_t)sms * (two_per_sm ? 2 : 1);
+  const int64_t slots_est = (int64_t)sms * ctas;
   int64_t per = est / (slots_est * 5) + 1;
   int64_t unit = ((per + kRows - 1) / kRows) * kRows;
   if (unit < 16 * kRows) unit = 16 * kRows;
@@ -475,7 +488,7 @@ int launch_wgrad_tc(const void* in, int64_t n_in, const void* gout, int64_t n_ou
   p.unit_pairs = (int)unit;
   const size_t smem = (size_t)stages * stage + 1024;
   int64_t max_units = (n_pairs_bound / unit + n_seg) * p.m_tiles;
-  const int64_t slots = (int64_t)sms * (two_per_sm ? 2 : 1);
+  const int64_t slots = (int64_t)sms * ctas;
   int grid = (int)(max_units < slots ? (max_units < 1 ? 1 : max_units) : slots);
   // Both operands fetched by the TMA unit (tile::gather4) where it measured faster than cp.async
   // (profiles/r2_gather4_validation.txt, batch 4: C_out <= 128 layers 3-23 % faster, 256-channel layers
