@@ -127,8 +127,9 @@ struct Ring {
   }
 };
 
-template <int T>
-__global__ void __launch_bounds__(128 * T + 192) gather_gemm_tc4_kernel(
+// kMinBlocks: CTAs per SM the register allocation must allow (3 caps the kernel at 68 registers per thread)
+template <int T, int kMinBlocks>
+__global__ void __launch_bounds__(128 * T + 192, kMinBlocks) gather_gemm_tc4_kernel(
     const Params p, const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm32) {
   constexpr int kProdWarps = 4 * T;
   constexpr int kRows = kTileM * T;
@@ -545,17 +546,17 @@ static bool make_row_map(CUtensorMap* tm, const void* base, int64_t rows, int co
   return r == CUDA_SUCCESS;
 }
 
-template <int T>
+template <int T, int kMinBlocks>
 static cudaError_t launch_variant(const Params& p, const CUtensorMap& tm64, const CUtensorMap& tm32, int grid,
                                   size_t smem, cudaStream_t st) {
   static size_t opted_in = 0;                      // per instantiation
   if (smem > opted_in) {
-    cudaError_t e = cudaFuncSetAttribute(gather_gemm_tc4_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gather_gemm_tc4_kernel<T, kMinBlocks>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     opted_in = smem;
   }
-  gather_gemm_tc4_kernel<T><<<grid, 128 * T + 192, smem, st>>>(p, tm64, tm32);
+  gather_gemm_tc4_kernel<T, kMinBlocks><<<grid, 128 * T + 192, smem, st>>>(p, tm64, tm32);
   return cudaSuccess;
 }
 
@@ -622,30 +623,45 @@ int launch_gather_gemm_tc4(const void* in, int64_t n_src, const void* wt, int k,
   p.acc_stride = stride;
   B2S_REQUIRE(stride * T <= 512, B2S_ERR_UNSUPPORTED, "b2s_conv_gather_gemm: C_res %d with %d-row tiles", c_res,
               tile_rows);
-  p.acc_bufs = stride * T * 2 <= 512 ? 2 : 1;
-  p.tmem_cols = stride * T * p.acc_bufs;
   const int crp = ((c_res + 7) / 8) * 8;
-  // shared memory per SM: 228 KiB, 1 KiB reserved per CTA; this kernel has ~5 KiB of static smem (barriers +
-  // the batch-norm partial sums) and 1 KiB of alignment slack -> two CTAs per SM leave 107 KiB for each ring
-  const int budget2 = 107 * 1024, budget1 = 220 * 1024;
-  // 96-channel reductions: the 32-channel tail rides in the stage of the 64-channel chunk when two such
-  // stages still fit twice per SM
+  const int rowb_max = p.n64 ? 128 : 64;
+  const int plain_stride = (T * kABytes + crp * rowb_max + 1023) & ~1023;
   const int merged_stride = (T * (kABytes + kATail) + crp * 192 + 1023) & ~1023;
-  p.merge_tail = (p.n64 == 1 && p.tail32 && 2 * merged_stride <= budget2) ? 1 : 0;
+  bool may_merge = p.n64 == 1 && p.tail32;
   {
     const char* em = getenv("B2S_TC4_MERGE");
-    if (em && em[0] == '0') p.merge_tail = 0;
+    if (em && em[0] == '0') may_merge = false;
   }
-  const int rowb_max = p.n64 ? 128 : 64;
-  p.stage_stride = p.merge_tail ? merged_stride : ((T * kABytes + crp * rowb_max + 1023) & ~1023);
-  // two CTAs per SM when both the ring (>= 2 merged / 3 plain stages) and the TMEM columns fit twice
-  int ctas_per_sm = 1;
-  int stages = budget2 / p.stage_stride;
-  if (stages >= (p.merge_tail ? 2 : 3) && p.tmem_cols <= 256) {
-    ctas_per_sm = 2;
-  } else {
-    stages = budget1 / p.stage_stride;
+  // CTAs per SM.  Every CTA is one independent gather -> MMA -> epilogue chain, and the number of chains per SM,
+  // not the ring depth, is what hides the hand-shake and gather latencies (weight gradient: 1 x 4 stages ->
+  // 2 x 2 stages = -27 %, profiles/r2_wgrad_ctas.txt), so take the most CTAs that fit with >= 2 stages each:
+  // shared memory 228 KiB per SM, per CTA 1 KiB reserved + ~5 KiB static + 1 KiB alignment slack; TMEM 512
+  // columns per SM (a CTA needs T accumulators, double-buffered when they fit); three CTAs also need the
+  // 68-register variant.  96-channel reductions merge the 32-channel tail into the 64-channel stage when two
+  // such stages fit.
+  static const int max_ctas = [] {
+    const char* e = getenv("B2S_TC4_CTAS");
+    int v = e ? atoi(e) : 2;
+    return v < 1 ? 1 : (v > 3 ? 3 : v);
+  }();
+  int ctas_per_sm = 1, stages = 0;
+  p.merge_tail = 0;
+  p.acc_bufs = 1;
+  for (int c = (T == 1 ? max_ctas : (max_ctas > 2 ? 2 : max_ctas)); c >= 1; --c) {
+    const int budget = (228 * 1024) / c - 7 * 1024;
+    if (c * stride * T > 512 && c > 1) continue;
+    const bool merge = may_merge && 2 * merged_stride <= budget;
+    const int ss = merge ? merged_stride : plain_stride;
+    const int st_fit = budget / ss;
+    if (st_fit < 2 && c > 1) continue;
+    ctas_per_sm = c;
+    stages = st_fit;
+    p.merge_tail = merge ? 1 : 0;
+    p.stage_stride = ss;
+    p.acc_bufs = (c * stride * T * 2 <= 512) ? 2 : 1;
+    break;
   }
+  p.tmem_cols = stride * T * p.acc_bufs;
   if (stages > 8) stages = 8;
   p.dbg = 0;
   p.wait_ns = 0;
@@ -659,18 +675,16 @@ int launch_gather_gemm_tc4(const void* in, int64_t n_src, const void* wt, int k,
   }
   {
     const char* es = getenv("B2S_TC_STAGES");
-    if (es && atoi(es) >= 2 && atoi(es) <= 8 && atoi(es) * p.stage_stride <= budget1) {
-      stages = atoi(es);
-      ctas_per_sm = (stages * p.stage_stride <= budget2 && p.tmem_cols <= 256) ? 2 : 1;
-    }
+    if (es && atoi(es) >= 2 && atoi(es) <= stages) stages = atoi(es);
   }
   B2S_REQUIRE(stages >= 2, B2S_ERR_UNSUPPORTED, "b2s_conv_gather_gemm: tile does not fit (C=%d)", c_res);
   p.stages = stages;
   const size_t smem = (size_t)stages * p.stage_stride + 1024;
   int grid = persistent_sms() * ctas_per_sm;
   if (grid > p.n_tiles) grid = p.n_tiles;
-  cudaError_t e = T == 2 ? launch_variant<2>(p, tm64, tm32, grid, smem, st)
-                         : launch_variant<1>(p, tm64, tm32, grid, smem, st);
+  cudaError_t e = T == 2 ? launch_variant<2, 1>(p, tm64, tm32, grid, smem, st)
+                  : ctas_per_sm == 3 ? launch_variant<1, 3>(p, tm64, tm32, grid, smem, st)
+                                     : launch_variant<1, 2>(p, tm64, tm32, grid, smem, st);
   B2S_REQUIRE(e == cudaSuccess, B2S_ERR_CUDA, "b2s_conv_gather_gemm: cannot opt in to %zu B smem: %s", smem,
               cudaGetErrorString(e));
   return B2S_OK;
