@@ -82,7 +82,7 @@ def parse():
     ap.add_argument("--sync-bn", action="store_true")
     ap.add_argument("--sm-reserve", type=int, default=None,
                     help="SMs kept free of the persistent conv grids (default 0: measured at N = 2, reserving 8 / 16 "
-                         "SMs for NCCL LOSES 3 % - the all-reduce is not what limits scaling, profiles/r2_scaling.txt)")
+                         "SMs for NCCL LOSES 3 %% - the all-reduce is not what limits scaling, profiles/r2_scaling.txt)")
     ap.add_argument("--pool", type=int, default=4, help="distinct batches cycled per rank")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
