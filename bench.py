@@ -400,7 +400,9 @@ def main():
                                                         bucket_cap_mb=args.bucket_mb)
     # SGD momentum 0.9, weight decay 1e-4 (pcseg/optim/__init__.py:15-21 - the reference never passes
     # NESTEROV on), AMP GradScaler, clip 10 (train.py:367-372); lr is irrelevant to throughput
-    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    # fused=True: torch's multi-tensor SGD kernel takes the GradScaler's found_inf flag ON THE DEVICE, so
+    # scaler.step() does not read it back (one host sync per step less; the same optimizer for both arms)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4, fused=True)
     scaler = torch.amp.GradScaler("cuda", enabled=amp)
 
     # ---- synthetic data: a pool of distinct batches per rank, in pinned host memory

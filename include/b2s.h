@@ -196,6 +196,18 @@ int32_t b2s_conv_steps_supported(int32_t dtype, int64_t n_src, int32_t c_red, in
 int32_t b2s_conv_tile_rows(int32_t c_res, int64_t n_rows);
 int b2s_weight_to_kmajor(const void* weight_f16, int32_t k, int32_t c_in, int32_t c_out, void* out_f16,
                          b2s_stream_t stream);
+/* The fp16 operand copies of MANY fp32 master weights in one launch - what the reference does per conv call through
+ * custom_fwd(cast_inputs=torch.half) (TS/nn/functional/conv.py:19), done once per optimizer update for every
+ * registered parameter.  desc: DEVICE array of n descriptors; entry i owns the 32 x 32 tiles
+ * [unit_start, unit_start + k * ceil(c_in / 32) * ceil(c_out / 32)) of the launch (exclusive prefix sums, ascending);
+ * total_units = their sum.  cast_f16 / kmajor_f16 may be NULL.                                           */
+typedef struct b2s_weight_desc {
+  const float* src;     /* fp32 [k][c_in][c_out]                                        */
+  void* cast_f16;       /* fp16 [k][c_in][c_out]: operand of the input-gradient pass     */
+  void* kmajor_f16;     /* fp16 [k][c_out][c_in]: operand of the forward pass            */
+  int32_t k, c_in, c_out, unit_start;
+} b2s_weight_desc;
+int b2s_weights_refresh(const b2s_weight_desc* desc, int32_t n, int64_t total_units, b2s_stream_t stream);
 int b2s_conv_gather_gemm_steps(int32_t dtype, const void* in, int64_t n_src, const void* weight,
                                int32_t weight_kmajor, int32_t k, int32_t c_in, int32_t c_out,
                                int32_t transpose_w, int32_t flip_k, const int32_t* nbr,

@@ -46,6 +46,7 @@ _SIGNATURES = {
     "b2s_conv_steps_supported": (c_int32, [c_int32, c_int64, c_int32, c_int32]),
     "b2s_conv_tile_rows": (c_int32, [c_int32, c_int64]),
     "b2s_weight_to_kmajor": (c_int32, [_P, c_int32, c_int32, c_int32, _P, _P]),
+    "b2s_weights_refresh": (c_int32, [_P, c_int32, c_int64, _P]),
     "b2s_conv_gather_gemm_steps": (c_int32, [c_int32, _P, c_int64, _P, c_int32, c_int32, c_int32, c_int32,
                                              c_int32, c_int32, _P, _P, _P, _P, c_int32, _P, c_int64, _P, _P, _P,
                                              _P, c_size_t, _P]),

@@ -292,6 +292,15 @@ def weight_to_kmajor(w: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def weights_refresh(desc: torch.Tensor, total_units: int) -> None:
+    """One launch over a device descriptor table int64 [n, 5] = b2s_weight_desc (src, cast, kmajor pointers,
+    k | c_in << 32, c_out | unit_start << 32): fp32 masters -> fp16 parameter-layout and K-major copies."""
+    _cuda(desc)
+    assert desc.dtype == torch.int64 and desc.ndim == 2 and desc.shape[1] == 5 and desc.is_contiguous()
+    check(_lib.lib().b2s_weights_refresh(desc.data_ptr(), desc.shape[0], int(total_units), _stream()),
+          "weights_refresh")
+
+
 def kmap_pairs(nbr_out: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
     """(pairs int32 [K*N_out, 2] padded buffer, d_total int64 [1]) - reference pair order."""
     _cuda(nbr_out)

@@ -23,6 +23,7 @@ int launch_gather_gemm_tc(const void* in, int64_t n_src, const void* weight, int
                           void* ws, size_t ws_bytes, cudaStream_t st);
 size_t tc_gather_gemm_workspace(int k, int c_in, int c_out);
 void launch_weight_to_kmajor(const void* w, int k, int c_in, int c_out, void* out, cudaStream_t st);
+void launch_weights_refresh(const void* desc, int n, int64_t total_units, cudaStream_t st);
 int tc4_tile_rows(int c_res, int64_t n_rows);
 bool tc_wgrad_supported(int c_in, int c_out);
 int launch_wgrad_tc(const void* in, int64_t n_in, const void* gout, int64_t n_out, const int32_t* nbmaps,
@@ -62,6 +63,14 @@ int b2s_weight_to_kmajor(const void* weight, int32_t k, int32_t c_in, int32_t c_
   B2S_REQUIRE(weight && out && k >= 1 && c_in >= 1 && c_out >= 1, B2S_ERR_INVALID, "b2s_weight_to_kmajor: bad argument");
   launch_weight_to_kmajor(weight, k, c_in, c_out, out, as_stream(stream));
   B2S_CHECK_LAUNCH("b2s_weight_to_kmajor");
+  return B2S_OK;
+}
+
+int b2s_weights_refresh(const b2s_weight_desc* desc, int32_t n, int64_t total_units, b2s_stream_t stream) {
+  B2S_REQUIRE(desc && n >= 1 && total_units >= 1 && total_units < (int64_t)0x7FFFFFFF, B2S_ERR_INVALID,
+              "b2s_weights_refresh: bad argument");
+  launch_weights_refresh(desc, n, total_units, as_stream(stream));
+  B2S_CHECK_LAUNCH("b2s_weights_refresh");
   return B2S_OK;
 }
 

@@ -37,6 +37,51 @@ __global__ void __launch_bounds__(256) transpose_weight_kernel(const __half* __r
   }
 }
 
+// One launch for the fp16 operand copies of MANY fp32 master weights (b2s_weights_refresh): block = one 32 x 32
+// (c_in x c_out) tile of one offset of one weight; the fp32 tile is read once (coalesced over c_out), written as the
+// fp16 parameter layout [K][c_in][c_out] (the input gradient's operand) and, through shared memory, as the K-major
+// layout [K][c_out][c_in] (the forward operand).
+struct WeightDesc {
+  const float* src;
+  __half* cast;
+  __half* kmajor;
+  int k, c_in, c_out, unit_start;
+};
+static_assert(sizeof(WeightDesc) == 40, "b2s_weight_desc layout");
+
+__global__ void __launch_bounds__(256) weights_refresh_kernel(const WeightDesc* __restrict__ desc, int n) {
+  __shared__ __half tile[32][34];
+  const int u = blockIdx.x;
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (desc[mid].unit_start <= u) lo = mid; else hi = mid - 1;
+  }
+  const WeightDesc d = desc[lo];
+  const int tx_n = (d.c_out + 31) >> 5, ty_n = (d.c_in + 31) >> 5;
+  const int t = u - d.unit_start;
+  const int k = t / (tx_n * ty_n), r = t - k * (tx_n * ty_n);
+  if (k >= d.k) return;
+  const int y0 = (r / tx_n) << 5, x0 = (r % tx_n) << 5;      // y: c_in, x: c_out
+  const int64_t base = (int64_t)k * d.c_in * d.c_out;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int ci = y0 + j, co = x0 + tx;
+    __half h = __float2half(0.f);
+    if (ci < d.c_in && co < d.c_out) {
+      h = __float2half_rn(d.src[base + (int64_t)ci * d.c_out + co]);
+      if (d.cast) d.cast[base + (int64_t)ci * d.c_out + co] = h;
+    }
+    tile[j][tx] = h;
+  }
+  if (!d.kmajor) return;
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int co = x0 + j, ci = y0 + tx;
+    if (co < d.c_out && ci < d.c_in) d.kmajor[base + (int64_t)co * d.c_in + ci] = tile[tx][j];
+  }
+}
+
 static int tmem_cols_for(int n) {
   int c = 32;
   while (c < n) c <<= 1;
@@ -70,6 +115,10 @@ void launch_weight_to_kmajor(const void* w, int k, int c_in, int c_out, void* ou
   dim3 g((unsigned)ceil_div(c_out, 32), (unsigned)ceil_div(c_in, 32), (unsigned)k);
   tc::transpose_weight_kernel<<<g, 256, 0, st>>>(reinterpret_cast<const __half*>(w), reinterpret_cast<__half*>(out),
                                                  c_in, c_out);
+}
+
+void launch_weights_refresh(const void* desc, int n, int64_t total_units, cudaStream_t st) {
+  tc::weights_refresh_kernel<<<(unsigned)total_units, 256, 0, st>>>(reinterpret_cast<const tc::WeightDesc*>(desc), n);
 }
 
 // weight_kmajor != 0: `weight` already is the K-major B operand of this pass ([K][c_res][c_red]); otherwise it is

@@ -18,7 +18,7 @@ from torch import nn
 
 from .. import torchsparse as ts
 from ..torchsparse import nn as spnn
-from ..torchsparse.nn.functional import batch_norm_act, batch_norm_fusable
+from ..torchsparse.nn.functional import batch_norm_act, batch_norm_fusable, zero_sums
 from ..torchsparse import PointTensor
 from .losses import SegLoss
 from ..torchsparse.operators import _CatFeats
@@ -66,7 +66,7 @@ def _conv_bn(conv, bn, x, relu=True, residual=None):
     sums = None
     if batch_norm_fusable(torch.float16 if torch.is_autocast_enabled() else x.feats.dtype, bn):
         # the conv's epilogue accumulates the batch statistics of its own output rows (one [N, C] pass less)
-        sums = torch.zeros((2, bn.num_features), dtype=torch.float64, device=x.feats.device)
+        sums = zero_sums(bn.num_features, x.feats.device)
     y = conv(x, bn_sums=sums)
     return y._like(batch_norm_act(y.feats, bn, relu=relu, residual=residual))
 

@@ -14,6 +14,7 @@ from __future__ import annotations
 from typing import List, Optional, Tuple, Union
 
 import os
+import weakref
 
 import torch
 from torch.autograd import Function
@@ -22,7 +23,7 @@ from torch.autograd.function import once_differentiable
 from ... import backend as B
 from ..tensor import SparseTensor
 from ..utils import make_ntuple
-from .utils import fapply, get_kernel_offsets
+from .utils import fapply, get_kernel_offsets, kernel_offsets_cached
 
 __all__ = ["sphash", "sphashquery", "spcount", "spdownsample", "spvoxelize", "spdevoxelize",
            "calc_ti_weights", "conv3d", "relu", "leaky_relu", "KernelMap", "build_kernel_map"]
@@ -279,8 +280,7 @@ def _tile_order(coords: torch.Tensor) -> torch.Tensor:
 def build_kernel_map(in_coords: torch.Tensor, out_coords: torch.Tensor, kernel_size, in_stride,
                      dilation=1) -> KernelMap:
     kernel_size = make_ntuple(kernel_size, 3)
-    offsets = get_kernel_offsets(kernel_size, stride=in_stride, dilation=dilation,
-                                 device=in_coords.device)
+    offsets = kernel_offsets_cached(kernel_size, stride=in_stride, dilation=dilation, device=in_coords.device)
     same = (in_coords is out_coords) or (in_coords.data_ptr() == out_coords.data_ptr()
                                           and in_coords.shape == out_coords.shape)
     symmetric = bool(same and all(k % 2 == 1 for k in kernel_size))
@@ -310,11 +310,92 @@ def _weight_cache(weight: torch.Tensor, slot: str, make):
     return val
 
 
+class _WeightBank:
+    """fp16 operand copies (parameter layout for the input gradient, K-major for the forward pass) of every fp32
+    conv PARAMETER seen on a device, kept in persistent buffers and refreshed by ONE launch (b2s_weights_refresh)
+    the first time a parameter is looked up after the optimizer moved its version.  Per-parameter refresh cost
+    126 small launches per MinkUNet-34 step (cast + transpose per conv), each followed by a CPU-bound gap on
+    the device (scripts/step_timeline.py: ~2 ms idle per step around them)."""
+
+    class Entry:
+        __slots__ = ("ref", "cast", "kmajor", "key", "k", "c_in", "c_out")
+
+    def __init__(self, device):
+        self.device = device
+        self.entries = []
+        self.table = None               # (device int64 [n, 5], total units, the entries it describes)
+
+    @staticmethod
+    def _units(e):
+        return e.k * (-(-e.c_in // 32)) * (-(-e.c_out // 32))
+
+    def _launch(self, entries, table=None):
+        if table is None:
+            import numpy as np
+            rows, start = [], 0
+            for e in entries:
+                w = e.ref()
+                rows.append((w.data_ptr(), e.cast.data_ptr(), e.kmajor.data_ptr(), e.k | (e.c_in << 32),
+                             e.c_out | (start << 32)))
+                start += self._units(e)
+            table = (torch.from_numpy(np.asarray(rows, dtype=np.int64)).to(self.device), start)
+        B.weights_refresh(table[0], table[1])
+        for e in entries:
+            w = e.ref()
+            e.key = (w._version, w.data_ptr())
+        return table
+
+    def lookup(self, weight):
+        e = weight.__dict__.get("_b2s_bank")
+        if e is None or e.ref() is not weight:              # (a deep-copied parameter carries the original's entry)
+            e = _WeightBank.Entry()
+            e.ref = weakref.ref(weight)
+            shape3 = tuple(weight.shape) if weight.ndim == 3 else (1,) + tuple(weight.shape)
+            e.k, e.c_in, e.c_out = shape3
+            e.cast = torch.empty(weight.shape, dtype=torch.float16, device=weight.device)
+            e.kmajor = torch.empty((e.k, e.c_out, e.c_in), dtype=torch.float16, device=weight.device)
+            e.key = None
+            weight._b2s_bank = e
+            self.entries.append(e)
+            self.table = None
+            self._launch([e])                               # first sight: this parameter alone
+        elif e.key != (weight._version, weight.data_ptr()):
+            self.refresh_all()
+        return e
+
+    def refresh_all(self):
+        live = [e for e in self.entries if e.ref() is not None]
+        moved = any(e.key is None or e.key[1] != e.ref().data_ptr() for e in live)
+        if len(live) != len(self.entries) or moved or self.table is None or self.table[2] != len(live):
+            self.entries = live
+            self.table = None
+        t = self._launch(live, None if self.table is None else self.table[:2])
+        self.table = (t[0], t[1], len(live))
+
+
+_WEIGHT_BANKS = {}
+_WEIGHT_BANK = os.environ.get("B2S_WEIGHT_BANK", "1") != "0"
+
+
+def _banked(weight: torch.Tensor, dtype: torch.dtype):
+    """The bank entry of ``weight`` when it is an fp32 CUDA conv parameter used with fp16 features, else None."""
+    if not (_WEIGHT_BANK and dtype == torch.float16 and weight.dtype == torch.float32 and weight.is_cuda
+            and isinstance(weight, torch.nn.Parameter) and weight.ndim in (2, 3) and weight.is_contiguous()):
+        return None
+    bank = _WEIGHT_BANKS.get(weight.device)
+    if bank is None:
+        bank = _WEIGHT_BANKS[weight.device] = _WeightBank(weight.device)
+    return bank.lookup(weight)
+
+
 def _cast_weight(weight: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """fp32 master weight -> feature dtype (the reference re-casts on every call through custom_fwd,
     TS/nn/functional/conv.py:19)."""
     if weight.dtype == dtype:
         return weight
+    e = _banked(weight, dtype)
+    if e is not None:
+        return e.cast
     return _weight_cache(weight, "_b2s_cast_" + str(dtype).split(".")[-1], lambda: weight.detach().to(dtype))
 
 
@@ -323,6 +404,9 @@ def _kmajor_weight(weight: torch.Tensor, w_cast: torch.Tensor):
     first revision transposed the weight inside every forward call: 63 extra launches per step)."""
     if w_cast.dtype != torch.float16:
         return None
+    e = weight.__dict__.get("_b2s_bank") if hasattr(weight, "__dict__") else None
+    if e is not None and e.cast is w_cast and e.ref() is weight:
+        return e.kmajor
     w3 = w_cast if w_cast.ndim == 3 else w_cast.unsqueeze(0)
     return _weight_cache(weight, "_b2s_kmajor", lambda: B.weight_to_kmajor(w3.contiguous()))
 
@@ -430,6 +514,21 @@ def _pad_for_tensor_cores(feats: torch.Tensor, weight: torch.Tensor):
 
 
 _AUTO_BN_SUMS = os.environ.get("B2S_AUTO_BN_SUMS", "1") != "0"
+_ZERO_CHUNK = 1 << 16                   # doubles per memset: ~2 steps of MinkUNet-34's 55 statistics buffers
+_zero_arena = {}                        # device -> [chunk, next free element]
+
+
+def zero_sums(c: int, device) -> torch.Tensor:
+    """fp64 zeros [2, c] for a conv epilogue's batch-norm statistics, cut from a chunk zeroed by ONE memset
+    (a ``torch.zeros`` per conv was 55 fill launches per MinkUNet-34 step).  Every slice is handed out once."""
+    n = 2 * c
+    device = torch.device(device)
+    slot = _zero_arena.get(device)
+    if slot is None or slot[1] + n > slot[0].numel():
+        slot = _zero_arena[device] = [torch.zeros(max(_ZERO_CHUNK, n), dtype=torch.float64, device=device), 0]
+    out = slot[0][slot[1]: slot[1] + n].view(2, c)
+    slot[1] += n
+    return out
 
 
 def _auto_sums(bn_sums, feats, weight, keep_out, bias):
@@ -442,7 +541,7 @@ def _auto_sums(bn_sums, feats, weight, keep_out, bias):
     if not ok:
         return None
     if bn_sums is None and _AUTO_BN_SUMS and torch.is_grad_enabled() and weight.requires_grad:
-        bn_sums = torch.zeros((2, weight.shape[2]), dtype=torch.float64, device=feats.device)
+        bn_sums = zero_sums(weight.shape[2], feats.device)
     return bn_sums
 
 

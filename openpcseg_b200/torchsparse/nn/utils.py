@@ -51,3 +51,16 @@ def get_kernel_offsets(size, stride=1, dilation=1, device="cpu") -> torch.Tensor
     size, stride, dilation = (make_ntuple(size, ndim=3), make_ntuple(stride, ndim=3),
                               make_ntuple(dilation, ndim=3))
     return torch.from_numpy(_offsets_np(size, stride, dilation).copy()).to(device)
+
+
+_OFFSETS_DEV = {}
+
+
+def kernel_offsets_cached(size, stride=1, dilation=1, device="cpu") -> torch.Tensor:
+    """``get_kernel_offsets`` for this package's own READ-ONLY use: one device copy per (size, stride, dilation,
+    device) instead of a pageable host-to-device copy (a blocking call) per kernel map and per trilinear map."""
+    key = (make_ntuple(size, ndim=3), make_ntuple(stride, ndim=3), make_ntuple(dilation, ndim=3), torch.device(device))
+    hit = _OFFSETS_DEV.get(key)
+    if hit is None:
+        hit = _OFFSETS_DEV[key] = get_kernel_offsets(size, stride, dilation, device)
+    return hit

@@ -104,6 +104,41 @@ def test_reference_backend_names(ts):
     assert eq(B.hash_cuda(dev(c)), R.sphash(c))
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.float16, FP16_TOL)])
+@pytest.mark.parametrize("case", ["k3s1", "k2s2", "k2s2_transposed"])
+def test_reference_backend_conv_names(ts, case, dtype, tol):
+    """``backend.convolution_{forward,backward}_cuda`` with the REFERENCE's argument format (pair list
+    ``nbmaps`` [M, 2] = (in, out) grouped by offset + host ``nbsizes``; TS/backend/convolution/
+    convolution_cuda.cu:53-278, called from TS/nn/functional/conv.py:80-137) against the oracle."""
+    from openpcseg_b200 import backend as B
+    rng = np.random.default_rng(31)
+    c = multi_batch_cloud(9, n=1500, extent=40, batches=2)
+    c_in, c_out = 32, 64
+    if case == "k3s1":
+        lo, hi, ks, transposed = c, c, 3, False
+    else:
+        lo, hi, ks = c, R.spdownsample(c, 2, 2, 1), 2
+        transposed = case.endswith("transposed")
+    nbmaps, nbsizes = R.build_kmap(lo, hi, ks, 1)                 # (lo row, hi row) pairs
+    n_in, n_out = (len(hi), len(lo)) if transposed else (len(lo), len(hi))
+    x = rng.standard_normal((n_in, c_in)).astype(np.float32)
+    w = (rng.standard_normal((ks ** 3, c_in, c_out)) / np.sqrt(c_in * ks)).astype(np.float32)
+    g = rng.standard_normal((n_out, c_out)).astype(np.float32)
+    if dtype == torch.float16:                                    # the oracle sees the rounded operands
+        x, w, g = (a.astype(np.float16).astype(np.float32) for a in (x, w, g))
+    exp_y = R.conv_forward(x, w, nbmaps, nbsizes, (len(lo), len(hi)), transposed)
+    exp_gx, exp_gw = R.conv_backward(x, w, g, nbmaps, nbsizes, transposed)
+    nb_d, sz_h = dev(nbmaps.astype(np.int32)), torch.from_numpy(nbsizes.astype(np.int32))
+    xd, wd, gd = dev(x, dtype), dev(w, dtype), dev(g, dtype)
+    y = torch.zeros(n_out, c_out, device="cuda", dtype=dtype)
+    B.convolution_forward_cuda(xd, y, wd, nb_d, sz_h, transposed)
+    assert rel_err(y, exp_y) <= tol
+    gx, gw = torch.zeros_like(xd), torch.zeros_like(wd)
+    B.convolution_backward_cuda(xd, gx, gd, wd, gw, nb_d, sz_h, transposed)
+    assert rel_err(gx, exp_gx) <= tol
+    assert rel_err(gw, exp_gw) <= (tol if dtype == torch.float32 else 2 * tol)
+
+
 # --------------------------------------------------------------- coordinates and maps
 def test_unique_and_downsample(ts, golden):
     from openpcseg_b200 import backend as B

@@ -120,3 +120,63 @@ def test_chunked_pair_list_and_segmented_wgrad(use_perm):
     w_ref = B.conv_wgrad(x, gy, k, ref_pairs, km.nbsizes32, False)
     w_seg = B.conv_wgrad(x, gy, k, pairs, seg, False)
     assert float((w_ref - w_seg).abs().max()) <= 1e-4 * float(w_ref.abs().max())
+
+
+def test_weight_bank_refreshes_all_parameters_in_one_launch():
+    """The fp16 operand copies of the conv parameters (functional._WeightBank, b2s_weights_refresh): bit-exact
+    round-to-nearest casts in both layouts at first sight, refreshed for EVERY registered parameter when one is
+    looked up after an in-place update, with odd shapes (tile edges), a 2-D (1x1x1) weight and a dropped one."""
+    import gc
+    from openpcseg_b200.torchsparse.nn import functional as F
+    g = torch.Generator().manual_seed(3)
+    shapes = [(27, 96, 96), (8, 32, 64), (27, 40, 72), (1, 33, 17), (64, 128)]
+    params = [torch.nn.Parameter(torch.randn(*s, generator=g).cuda()) for s in shapes]
+
+    def check(p):
+        cast = F._cast_weight(p, torch.float16)
+        km = F._kmajor_weight(p, cast)
+        p3 = p.detach() if p.ndim == 3 else p.detach().unsqueeze(0)
+        assert cast.dtype == torch.float16 and torch.equal(cast, p.detach().half())
+        assert km.shape == (p3.shape[0], p3.shape[2], p3.shape[1]) and torch.equal(km, p3.half().transpose(1, 2))
+        return cast, km
+
+    bufs = [check(p) for p in params]
+    bank = F._WEIGHT_BANKS[params[0].device]
+    with torch.no_grad():
+        for p in params:
+            p.mul_(0.5).add_(0.123)                                   # optimizer-style in-place update
+    first = check(params[2])                                          # stale -> one launch refreshes all
+    n0 = len(bank.entries)                                            # (dead entries of earlier tests are gone now)
+    assert n0 >= len(params)
+    assert all(e.key == (e.ref()._version, e.ref().data_ptr()) for e in bank.entries if e.ref() is not None)
+    for p, (cast, km) in zip(params, bufs):
+        c2, k2 = check(p)
+        assert c2.data_ptr() == cast.data_ptr() and k2.data_ptr() == km.data_ptr()      # persistent buffers
+    assert first[0].data_ptr() == bufs[2][0].data_ptr()
+    dead = params.pop(1)
+    del dead, bufs
+    gc.collect()
+    with torch.no_grad():
+        params[0].add_(1.0)
+    check(params[0])
+    assert len(bank.entries) == n0 - 1                               # the dropped parameter left the table
+    for p in params:
+        check(p)
+    # a non-parameter (e.g. the zero-padded copy of a narrow layer) takes the per-call path
+    t = torch.randn(27, 32, 32, generator=g).cuda()
+    assert F._banked(t, torch.float16) is None
+    assert torch.equal(F._cast_weight(t, torch.float16), t.half())
+
+
+def test_zero_sums_slices_are_fresh_and_disjoint():
+    from openpcseg_b200.torchsparse.nn import functional as F
+    dev = torch.device("cuda", 0)
+    seen = []
+    for i in range(700):                                              # crosses several chunks
+        s = F.zero_sums(32 + 32 * (i % 8), dev)
+        assert s.shape == (2, 32 + 32 * (i % 8)) and s.dtype == torch.float64 and s.is_contiguous()
+        assert float(s.abs().sum()) == 0.0
+        s.fill_(float(i + 1))
+        seen.append(s)
+    for i, s in enumerate(seen):
+        assert bool((s == float(i + 1)).all())
