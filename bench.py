@@ -432,24 +432,54 @@ def main():
         scaler.update()
         return loss
 
+    copy_stream = torch.cuda.Stream(device=dev)
+    loss_host = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+
+    def upload(i):
+        """Host -> device copy of step i's inputs from pinned memory on the copy stream (so that it runs under the
+        previous step's kernels, as a prefetching loader with pin_memory does) + the event the step waits on."""
+        with torch.cuda.stream(copy_stream):
+            batch = {k: v.to(dev, non_blocking=True) for k, v in pool[i % len(pool)].items()}
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return batch, ev
+
     def run(n_steps, from_host):
-        """Returns (ms_total over the timed steps [device events, max over ranks], last loss value)."""
+        """Returns (ms_total over the timed steps [device events, max over ranks], last loss value).
+        from_host: every step's inputs are copied from pinned host memory and every step's loss is copied back to
+        the host INSIDE the timed region; the loss of step i is read by the host while step i + 1 is queued (an
+        asynchronous copy into pinned memory + an event), so the host never drains the device mid-run."""
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        last = None
+        main_stream = torch.cuda.current_stream(dev)
+        last, nxt, read_ev = None, None, [None, None]
         ev0.record()
+        if from_host:
+            nxt = upload(0)
         for i in range(n_steps):
             flush_buf.zero_()                              # L2 flush between iterations
             if from_host:
-                src = pool[i % len(pool)]
-                batch = {k: v.to(dev, non_blocking=True) for k, v in src.items()}
+                batch, ready = nxt
+                main_stream.wait_event(ready)
+                for t in batch.values():
+                    t.record_stream(main_stream)
+                if i + 1 < n_steps:
+                    nxt = upload(i + 1)
             else:
                 batch = resident[i % len(resident)]
             loss = step(batch)
             if from_host:
-                last = float(loss.item())                  # D2H of the step's result
+                loss_host[i % 2].copy_(loss.detach().float().reshape(1), non_blocking=True)   # D2H of the step's result
+                read_ev[i % 2] = torch.cuda.Event()
+                read_ev[i % 2].record(main_stream)
+                if i > 0:
+                    read_ev[(i - 1) % 2].synchronize()
+                    last = float(loss_host[(i - 1) % 2][0])
+        if from_host and n_steps > 0:
+            read_ev[(n_steps - 1) % 2].synchronize()
+            last = float(loss_host[(n_steps - 1) % 2][0])
         ev1.record()
         torch.cuda.synchronize()
         if world > 1:

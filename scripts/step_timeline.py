@@ -29,7 +29,7 @@ def main():
     from openpcseg_b200.synthetic import make_model_batch
     dev = torch.device("cuda", 0)
     model = MinkUNet(minkunet34_config()).to(dev).train()
-    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4, fused=True)
     scaler = torch.amp.GradScaler("cuda")
     pool = []
     for p in range(a.pool):
