@@ -510,7 +510,7 @@ def main():
         conv = prof.summarise()
 
     # ---- timed region 2: end to end from pinned host buffers
-    run(2, True)
+    run(max(2, 2 * len(pool)), True)          # the copy stream has its own allocator pool: let it see every batch size
     ms_e2e, last_loss = run(args.steps, True)
 
     value = D.whole_job_rate(args.batch * args.steps, world, ms_dev)
