@@ -323,6 +323,8 @@ class _WeightBank:
     def __init__(self, device):
         self.device = device
         self.entries = []
+        self.by_id = {}                 # id(parameter) -> entry (nothing is attached to the parameter itself: its
+        #                                 __dict__ is pickled by torch.save(model))
         self.table = None               # (device int64 [n, 5], total units, the entries it describes)
 
     @staticmethod
@@ -346,8 +348,8 @@ class _WeightBank:
         return table
 
     def lookup(self, weight):
-        e = weight.__dict__.get("_b2s_bank")
-        if e is None or e.ref() is not weight:              # (a deep-copied parameter carries the original's entry)
+        e = self.by_id.get(id(weight))
+        if e is None or e.ref() is not weight:              # (ids are re-used once a parameter is gone)
             e = _WeightBank.Entry()
             e.ref = weakref.ref(weight)
             shape3 = tuple(weight.shape) if weight.ndim == 3 else (1,) + tuple(weight.shape)
@@ -355,7 +357,7 @@ class _WeightBank:
             e.cast = torch.empty(weight.shape, dtype=torch.float16, device=weight.device)
             e.kmajor = torch.empty((e.k, e.c_out, e.c_in), dtype=torch.float16, device=weight.device)
             e.key = None
-            weight._b2s_bank = e
+            self.by_id[id(weight)] = e
             self.entries.append(e)
             self.table = None
             self._launch([e])                               # first sight: this parameter alone
@@ -368,6 +370,7 @@ class _WeightBank:
         moved = any(e.key is None or e.key[1] != e.ref().data_ptr() for e in live)
         if len(live) != len(self.entries) or moved or self.table is None or self.table[2] != len(live):
             self.entries = live
+            self.by_id = {id(e.ref()): e for e in live}
             self.table = None
         t = self._launch(live, None if self.table is None else self.table[:2])
         self.table = (t[0], t[1], len(live))
@@ -377,10 +380,14 @@ _WEIGHT_BANKS = {}
 _WEIGHT_BANK = os.environ.get("B2S_WEIGHT_BANK", "1") != "0"
 
 
+def _bankable(weight: torch.Tensor, dtype: torch.dtype) -> bool:
+    return (_WEIGHT_BANK and dtype == torch.float16 and weight.dtype == torch.float32 and weight.is_cuda
+            and isinstance(weight, torch.nn.Parameter) and weight.ndim in (2, 3) and weight.is_contiguous())
+
+
 def _banked(weight: torch.Tensor, dtype: torch.dtype):
     """The bank entry of ``weight`` when it is an fp32 CUDA conv parameter used with fp16 features, else None."""
-    if not (_WEIGHT_BANK and dtype == torch.float16 and weight.dtype == torch.float32 and weight.is_cuda
-            and isinstance(weight, torch.nn.Parameter) and weight.ndim in (2, 3) and weight.is_contiguous()):
+    if not _bankable(weight, dtype):
         return None
     bank = _WEIGHT_BANKS.get(weight.device)
     if bank is None:
@@ -404,9 +411,11 @@ def _kmajor_weight(weight: torch.Tensor, w_cast: torch.Tensor):
     first revision transposed the weight inside every forward call: 63 extra launches per step)."""
     if w_cast.dtype != torch.float16:
         return None
-    e = weight.__dict__.get("_b2s_bank") if hasattr(weight, "__dict__") else None
-    if e is not None and e.cast is w_cast and e.ref() is weight:
-        return e.kmajor
+    if _bankable(weight, torch.float16):
+        bank = _WEIGHT_BANKS.get(weight.device)
+        e = bank.by_id.get(id(weight)) if bank is not None else None
+        if e is not None and e.cast is w_cast and e.ref() is weight:
+            return e.kmajor
     w3 = w_cast if w_cast.ndim == 3 else w_cast.unsqueeze(0)
     return _weight_cache(weight, "_b2s_kmajor", lambda: B.weight_to_kmajor(w3.contiguous()))
 

@@ -29,3 +29,42 @@ def test_slice_cols_paths_and_partial_grads():
     b = torch.randn(5, 8)                                            # no grad wanted for b
     _CatFeats.apply(a, b).sum().backward()
     assert torch.equal(a.grad, torch.ones(5, 8))
+
+
+def test_weight_bank_host_logic(monkeypatch):
+    """functional._WeightBank without a GPU (the launch is recorded, not run): one single-entry launch at first
+    sight, ONE launch over every live parameter when a stale one is looked up, descriptor prefix sums in 32 x 32
+    tiles, dead parameters leave the table, nothing is attached to the parameter (it stays picklable)."""
+    import gc
+    import pickle
+    import openpcseg_b200.torchsparse.nn.functional as F
+    calls = []
+    monkeypatch.setattr(F.B, "weights_refresh", lambda table, total: calls.append((table.clone(), total)))
+    bank = F._WeightBank(torch.device("cpu"))
+    ps = [torch.nn.Parameter(torch.randn(27, 32, 64)), torch.nn.Parameter(torch.randn(8, 40, 72)),
+          torch.nn.Parameter(torch.randn(64, 128))]
+    es = [bank.lookup(p) for p in ps]
+    assert [(c[0].shape[0], c[1]) for c in calls] == [(1, 27 * 1 * 2), (1, 8 * 2 * 3), (1, 1 * 2 * 4)]
+    assert es[2].kmajor.shape == (1, 128, 64) and es[1].cast.shape == (8, 40, 72)
+    assert bank.lookup(ps[0]) is es[0] and len(calls) == 3                 # fresh: no launch
+    with torch.no_grad():
+        ps[1].add_(1.0)
+    assert bank.lookup(ps[1]) is es[1]
+    table, total = calls[-1]
+    assert table.shape == (3, 5) and total == 54 + 48 + 8
+    assert table[:, 0].tolist() == [p.data_ptr() for p in ps]
+    assert (table[:, 3] & 0xFFFFFFFF).tolist() == [27, 8, 1] and (table[:, 3] >> 32).tolist() == [32, 40, 64]
+    assert (table[:, 4] & 0xFFFFFFFF).tolist() == [64, 72, 128] and (table[:, 4] >> 32).tolist() == [0, 54, 102]
+    n = len(calls)
+    bank.lookup(ps[2])
+    assert len(calls) == n                                                  # refreshed together with ps[1]
+    del es
+    gone = ps.pop(1)
+    del gone
+    gc.collect()
+    with torch.no_grad():
+        ps[0].mul_(2.0)
+    bank.lookup(ps[0])
+    assert calls[-1][0].shape[0] == 2 and calls[-1][1] == 54 + 8 and len(bank.by_id) == 2
+    pickle.dumps(ps[0])
+    assert not F._bankable(torch.randn(27, 32, 32), torch.float16)         # not a Parameter / not CUDA
