@@ -23,8 +23,9 @@ reference) over one batch of B synthetic SemanticKITTI-shaped scans (64 x 1875 r
 
 Prints ONE JSON line:
   value         scans/s over all GPUs, inputs resident in HBM when the timed region starts
-  e2e           the same through the public API with pinned HOST buffers: H2D of the batch and D2H of the
-                loss inside the timed region
+  e2e           the same through the public API with pinned HOST buffers: every step's batch is copied host ->
+                device (copy stream, one step ahead) and every step's loss device -> host (asynchronously, read by
+                the host one step late), all inside the timed region
   roofline      the dominant conv kernel family timed live with CUDA events around every launch, in a
                 repeat of the same K steps after the `value` region
   cpu_baseline  the reference's CPU path on a bounded sub-scan (rank 0, N=1)
