@@ -68,3 +68,19 @@ def test_weight_bank_host_logic(monkeypatch):
     assert calls[-1][0].shape[0] == 2 and calls[-1][1] == 54 + 8 and len(bank.by_id) == 2
     pickle.dumps(ps[0])
     assert not F._bankable(torch.randn(27, 32, 32), torch.float16)         # not a Parameter / not CUDA
+
+
+def test_zero_sums_and_cached_offsets_host_logic():
+    import openpcseg_b200.torchsparse.nn.functional as F
+    from openpcseg_b200.torchsparse.nn.utils import get_kernel_offsets, kernel_offsets_cached
+    seen = [F.zero_sums(32 * (1 + i % 8), "cpu") for i in range(600)]      # several chunks
+    for i, s in enumerate(seen):
+        assert s.shape == (2, 32 * (1 + i % 8)) and s.dtype == torch.float64 and s.is_contiguous()
+        assert float(s.abs().sum()) == 0.0
+        s.fill_(i + 1.0)
+    assert all(bool((s == i + 1.0).all()) for i, s in enumerate(seen))      # slices never overlap
+    big = F.zero_sums(F._ZERO_CHUNK, "cpu")                                  # wider than a chunk
+    assert big.shape == (2, F._ZERO_CHUNK) and float(big.abs().sum()) == 0.0
+    a = kernel_offsets_cached(3, 2, 1, "cpu")
+    assert a is kernel_offsets_cached((3, 3, 3), (2, 2, 2), (1, 1, 1), torch.device("cpu"))
+    assert torch.equal(a, get_kernel_offsets(3, 2, 1, "cpu")) and a is not get_kernel_offsets(3, 2, 1, "cpu")
