@@ -84,3 +84,27 @@ def test_zero_sums_and_cached_offsets_host_logic():
     a = kernel_offsets_cached(3, 2, 1, "cpu")
     assert a is kernel_offsets_cached((3, 3, 3), (2, 2, 2), (1, 1, 1), torch.device("cpu"))
     assert torch.equal(a, get_kernel_offsets(3, 2, 1, "cpu")) and a is not get_kernel_offsets(3, 2, 1, "cpu")
+
+
+def test_batch_norm_act_fallback_with_sparse_wrappers():
+    """the fallback of batch_norm_act must run the DENSE batch norm of the module's class on
+    the [N, C] rows - MinkUNet's norms are SparseTensor wrappers (segmentors/minkunet.py _SparseBN) whose own
+    forward expects a SparseTensor.  Eval mode and CPU rows both take the fallback."""
+    from openpcseg_b200.segmentors.minkunet import _SparseBN
+    from openpcseg_b200.torchsparse.nn.functional import batch_norm_act
+    torch.manual_seed(0)
+    x, res = torch.randn(10, 8), torch.randn(10, 8)
+    bn = _SparseBN(8)
+    with torch.no_grad():
+        bn.running_mean.normal_()
+        bn.running_var.uniform_(0.5, 2.0)
+        bn.weight.normal_()
+        bn.bias.normal_()
+    ref = torch.nn.BatchNorm1d(8)
+    ref.load_state_dict(bn.state_dict())
+    y = batch_norm_act(x, bn.eval(), relu=True, residual=res)
+    assert torch.allclose(y, torch.relu(ref.eval()(x) + res), atol=1e-6)
+    bn.train(), ref.train()
+    y = batch_norm_act(x, bn, relu=False)                                   # CPU rows: stock training-mode path
+    assert torch.allclose(y, ref(x), atol=1e-6)
+    assert torch.allclose(bn.running_mean, ref.running_mean) and int(bn.num_batches_tracked) == 1
